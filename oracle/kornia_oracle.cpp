@@ -1,0 +1,1012 @@
+// oracle/kornia_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A CPU restatement (C++17) of the kornia-rs `kornia-imgproc` pixel-kernel hot
+// path named in BASELINE.json:north_star.  Every function cites the reference
+// file:line it follows (paths relative to /root/reference/crates/kornia-imgproc/src).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+// arm may load this library — and only as the checker / the CPU number that is
+// reported beside the GPU number.  The product path (kornia-rs_b200/, the
+// C-ABI libkornia_b200.so) never links or calls anything in here.
+//
+// PARITY STATUS: pinned.  The Rust reference cannot be built in this image (no
+// cargo/rustc), so the oracle is pinned against the reference's own in-tree
+// known-answer tests (transcribed into tests/test_oracle_golden.py with the
+// file:line of each) and against cv2 fixtures for the NV12 Q20 decode (the
+// reference states byte-parity with cv2 for that path).
+//
+// Build rules that matter for bit-level parity with the Rust code:
+//   * -ffp-contract=off : rustc never contracts a*b+c into an fma; neither do we.
+//     Where the reference's x86 leaf *does* call an FMA intrinsic
+//     (_mm256_fmadd_ps), we call fmaf() explicitly ("leaf" selectors below).
+//   * no -ffast-math; IEEE division and sqrt everywhere.
+//   * expf from the platform libm, like Rust's f32::exp on Linux.
+//
+// Threading mirrors the reference's rayon chunking (16-row tasks; 8-row tasks
+// in the fused resize; strip split above 1 Mpx for colour ops) with OpenMP so
+// that the timed CPU baseline uses all host cores the way the reference does.
+// Functions the reference runs single-threaded (separable_filter, sobel,
+// std_mean, find_min_max) are single-threaded here too unless the caller asks
+// for the "mt" variant.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define KO_API extern "C" __attribute__((visibility("default")))
+
+// leaf selectors: which CPU leaf of the reference to mirror where scalar and
+// SIMD leaves round differently (FMA vs mul+add).
+enum { KO_LEAF_SCALAR = 0, KO_LEAF_X86_AVX2_FMA = 1, KO_LEAF_AARCH64_NEON = 2 };
+
+KO_API int ko_version() { return 1; }
+
+KO_API void ko_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+KO_API int ko_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// Deterministic input generators used by the reference's GPU-parity tests.
+// cuda/color/mod.rs:303-321 (pattern_u8 / pattern_f32).  `seed` generalises the
+// fixed 0x12345678 so batches can use one pattern per image.
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API void ko_pattern_u8(uint8_t* out, size_t len, uint32_t seed) {
+    static const uint8_t prefix[15] = {0, 255, 255, 0, 0, 0, 255, 255, 255, 1, 254, 128, 128, 128, 64};
+    size_t n = std::min<size_t>(15, len);
+    for (size_t i = 0; i < n; ++i) out[i] = prefix[i];
+    uint32_t state = seed;
+    for (size_t i = n; i < len; ++i) {
+        state = state * 1664525u + 1013904223u;
+        out[i] = (uint8_t)(state >> 24);
+    }
+}
+
+KO_API void ko_pattern_f32(float* out, size_t len, uint32_t seed) {
+    std::vector<uint8_t> tmp(len);
+    ko_pattern_u8(tmp.data(), len, seed);
+    for (size_t i = 0; i < len; ++i) out[i] = (float)tmp[i] / 255.0f;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a8: gray_from_rgb  — color/gray/kernels.rs
+// ─────────────────────────────────────────────────────────────────────────────
+static const float RW_F32 = 0.299f, GW_F32 = 0.587f, BW_F32 = 0.114f;  // kernels.rs:2-4
+
+// f32: scalar leaf kernels.rs:405-410 (`rw*r + gw*g + bw*b`, left to right,
+// unfused); x86 AVX2+FMA leaf kernels.rs:338-402: fma(r,rw, fma(g,gw, b*bw)) for
+// the 8-px bulk, scalar expression for the npixels%8 tail.  Strips
+// (kernel_common.rs:51-78) are 8-px aligned so only the global tail is scalar.
+KO_API void ko_gray_from_rgb_f32(const float* src, float* dst, size_t npixels, int leaf) {
+    size_t bulk = 0;
+    if (leaf == KO_LEAF_X86_AVX2_FMA || leaf == KO_LEAF_AARCH64_NEON) bulk = npixels & ~(size_t)7;
+#pragma omp parallel for schedule(static) if (npixels >= 1024 * 1024)
+    for (long long i = 0; i < (long long)npixels; ++i) {
+        const float r = src[3 * i], g = src[3 * i + 1], b = src[3 * i + 2];
+        if ((size_t)i < bulk) {
+            dst[i] = fmaf(r, RW_F32, fmaf(g, GW_F32, b * BW_F32));
+        } else {
+            dst[i] = RW_F32 * r + GW_F32 * g + BW_F32 * b;
+        }
+    }
+}
+
+// u8: kernels.rs:229-238  (4899R + 9617G + 1868B + 8192) >> 14
+KO_API void ko_gray_from_rgb_u8(const uint8_t* src, uint8_t* dst, size_t npixels) {
+#pragma omp parallel for schedule(static) if (npixels >= 1024 * 1024)
+    for (long long i = 0; i < (long long)npixels; ++i) {
+        const uint32_t r = src[3 * i], g = src[3 * i + 1], b = src[3 * i + 2];
+        dst[i] = (uint8_t)((4899u * r + 9617u * g + 1868u * b + 8192u) >> 14);
+    }
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a9: rgb_from_nv12 / rgb_from_yuyv — color/yuv/kernels.rs:707-737 (decode_px,
+// yy_term), :945-966 (packed422 row), :1036-1069 (planar420 block), :1195-1221
+// (chroma_at), color/yuv/mod.rs:209-241 (entry points).
+// ─────────────────────────────────────────────────────────────────────────────
+static inline int32_t yy_term(int32_t y) { return std::max(y - 16, 0) * 1220542; }  // :734-737
+
+static inline void decode_px(int32_t yy, int32_t u, int32_t v, uint8_t* r, uint8_t* g, uint8_t* b) {  // :718-730
+    u -= 128;
+    v -= 128;
+    const int32_t bb = (yy + 2116026 * u + (1 << 19)) >> 20;
+    const int32_t gg = (yy + (-409993) * u + (-852492) * v + (1 << 19)) >> 20;
+    const int32_t rr = (yy + 1673527 * v + (1 << 19)) >> 20;
+    *r = (uint8_t)std::min(std::max(rr, 0), 255);
+    *g = (uint8_t)std::min(std::max(gg, 0), 255);
+    *b = (uint8_t)std::min(std::max(bb, 0), 255);
+}
+
+// src = Y plane (w*h) followed by interleaved UV (w*h/2); dst RGB8 HWC.
+KO_API int ko_rgb_from_nv12_u8(const uint8_t* src, uint8_t* dst, size_t w, size_t h) {
+    if ((w & 1) || (h & 1)) return -1;
+    const uint8_t* y = src;
+    const uint8_t* uv = src + w * h;
+    const size_t cw = w / 2;
+#pragma omp parallel for schedule(static) if (w * h >= 1024 * 1024)
+    for (long long cy = 0; cy < (long long)(h / 2); ++cy) {
+        const uint8_t* y_top = y + (2 * cy) * w;
+        const uint8_t* y_bot = y + (2 * cy + 1) * w;
+        uint8_t* d_top = dst + (2 * cy) * w * 3;
+        uint8_t* d_bot = dst + (2 * cy + 1) * w * 3;
+        for (size_t cx = 0; cx < cw; ++cx) {
+            const size_t idx = cy * cw * 2 + cx * 2;
+            const int32_t u = uv[idx], v = uv[idx + 1];
+            const size_t x = cx * 2;
+            for (size_t dx = 0; dx < 2; ++dx) {
+                const size_t dt = (x + dx) * 3;
+                decode_px(yy_term(y_top[x + dx]), u, v, &d_top[dt], &d_top[dt + 1], &d_top[dt + 2]);
+                decode_px(yy_term(y_bot[x + dx]), u, v, &d_bot[dt], &d_bot[dt + 1], &d_bot[dt + 2]);
+            }
+        }
+    }
+    return 0;
+}
+
+// YUYV packed 4:2:2 (`Y0 U Y1 V`), 2 bytes/px.
+KO_API int ko_rgb_from_yuyv_u8(const uint8_t* src, uint8_t* dst, size_t w, size_t h) {
+    if (w & 1) return -1;
+#pragma omp parallel for schedule(static) if (w * h >= 1024 * 1024)
+    for (long long row = 0; row < (long long)h; ++row) {
+        const uint8_t* s = src + row * w * 2;
+        uint8_t* d = dst + row * w * 3;
+        for (size_t g = 0; g < w / 2; ++g) {
+            const size_t base = g * 4;
+            const int32_t y0 = s[base], u = s[base + 1], y1 = s[base + 2], v = s[base + 3];
+            decode_px(yy_term(y0), u, v, &d[g * 6], &d[g * 6 + 1], &d[g * 6 + 2]);
+            decode_px(yy_term(y1), u, v, &d[g * 6 + 3], &d[g * 6 + 4], &d[g * 6 + 5]);
+        }
+    }
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// Shared samplers — interpolation/bilinear.rs:16-66, interpolation/nearest.rs:15-30
+// ─────────────────────────────────────────────────────────────────────────────
+static inline float bilinear_interpolation(const float* img, size_t rows, size_t cols, size_t C, float u, float v,
+                                           size_t c) {
+    const size_t iu = (size_t)truncf(u);
+    const size_t iv = (size_t)truncf(v);
+    const float frac_u = u - truncf(u);  // f32::fract
+    const float frac_v = v - truncf(v);
+    const float val00 = img[(iv * cols + iu) * C + c];
+    const float val01 = (iu + 1 < cols) ? img[(iv * cols + iu + 1) * C + c] : val00;
+    const float val10 = (iv + 1 < rows) ? img[((iv + 1) * cols + iu) * C + c] : val00;
+    const float val11 = (iu + 1 < cols && iv + 1 < rows) ? img[((iv + 1) * cols + iu + 1) * C + c] : val00;
+    const float frac_uu = 1.0f - frac_u;
+    const float frac_vv = 1.0f - frac_v;
+    const float w00 = frac_vv * frac_uu;
+    const float w10 = frac_vv * frac_u;
+    const float w01 = frac_v * frac_uu;
+    const float w11 = frac_v * frac_u;
+    return w00 * val00 + w10 * val01 + w01 * val10 + w11 * val11;
+}
+
+static inline float nearest_neighbor_interpolation(const float* img, size_t rows, size_t cols, size_t C, float u,
+                                                   float v, size_t c) {
+    // `u.round() as usize` (half away from zero; saturating cast) then clamp.
+    float ru = roundf(u), rv = roundf(v);
+    size_t iu = ru <= 0.0f ? 0 : (size_t)ru;
+    size_t iv = rv <= 0.0f ? 0 : (size_t)rv;
+    iu = std::min(iu, cols - 1);
+    iv = std::min(iv, rows - 1);
+    return img[(iv * cols + iu) * C + c];
+}
+
+enum { KO_NEAREST = 0, KO_BILINEAR = 1 };
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a1: resize::resize<C>(src,dst,mode) — resize/mod.rs:114-207
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API int ko_resize_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh, size_t C,
+                         int mode) {
+    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;
+    if (sw == dw && sh == dh) {  // :134-137
+        std::memcpy(dst, src, sw * sh * C * sizeof(float));
+        return 0;
+    }
+    // axis_lut :169-176 — a*x + b, a = src/dst, b = 0.5a - 0.5, clamp to [0, src-1]
+    auto axis_lut = [](size_t src_len, size_t dst_len) {
+        std::vector<float> v(dst_len);
+        const float a = (float)src_len / (float)dst_len;
+        const float b = 0.5f * a - 0.5f;
+        const float mx = (float)(src_len - 1);
+        for (size_t i = 0; i < dst_len; ++i) {
+            float s = a * (float)i + b;
+            // f32::clamp(0, max)
+            if (s < 0.0f) s = 0.0f;
+            if (s > mx) s = mx;
+            v[i] = s;
+        }
+        return v;
+    };
+    const std::vector<float> xs = axis_lut(sw, dw), ys = axis_lut(sh, dh);
+    const long long nchunks = (long long)((dh + 15) / 16);  // parallel.rs ROWS_PER_TASK = 16
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ck = 0; ck < nchunks; ++ck) {
+        const size_t y_end = std::min<size_t>(dh, (size_t)(ck + 1) * 16);
+        for (size_t y = (size_t)ck * 16; y < y_end; ++y) {
+            for (size_t x = 0; x < dw; ++x) {
+                float* px = dst + (y * dw + x) * C;
+                for (size_t k = 0; k < C; ++k) {
+                    px[k] = (mode == KO_BILINEAR) ? bilinear_interpolation(src, sh, sw, C, xs[x], ys[y], k)
+                                                  : nearest_neighbor_interpolation(src, sh, sw, C, xs[x], ys[y], k);
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a2: resize_normalize_to_tensor_u8_to_f32_bilinear — resize/fused.rs:147-228,
+// scalar leaf :273-318, AVX2 leaf :414-497 (FMA form on the dst_w&~7 bulk),
+// exact-2× box path :57-127 with scalar leaf :528-559 and AVX2 leaf (FMA on the
+// dst_w&~15 bulk).  NormalizeParams::from_mean_std :28-37.
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API void ko_normalize_params_from_mean_std(const float mean[3], const float stdv[3], float scale[3],
+                                              float bias[3]) {
+    for (int c = 0; c < 3; ++c) {
+        scale[c] = 1.0f / (stdv[c] * 255.0f);
+        bias[c] = -mean[c] / stdv[c];
+    }
+}
+
+static void fused_2x(const uint8_t* src, size_t sw, size_t /*sh*/, float* dst, size_t dw, size_t dh,
+                     const float scale[3], const float bias[3], int leaf) {
+    const size_t src_stride = sw * 3, plane = dw * dh;
+    const float s4[3] = {scale[0] * 0.25f, scale[1] * 0.25f, scale[2] * 0.25f};
+    size_t bulk = 0;
+    if (leaf == KO_LEAF_X86_AVX2_FMA || leaf == KO_LEAF_AARCH64_NEON) bulk = dw & ~(size_t)15;
+    const long long nchunks = (long long)((dh + 7) / 8);  // ROWS_PER_TASK = 8 (:104)
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ck = 0; ck < nchunks; ++ck) {
+        const size_t y_end = std::min<size_t>(dh, (size_t)(ck + 1) * 8);
+        for (size_t y = (size_t)ck * 8; y < y_end; ++y) {
+            const uint8_t* r0 = src + (2 * y) * src_stride;
+            const uint8_t* r1 = src + (2 * y + 1) * src_stride;
+            for (size_t x = 0; x < dw; ++x) {
+                const size_t b0 = 2 * x * 3, b1 = b0 + 3;
+                for (int c = 0; c < 3; ++c) {
+                    const uint32_t sum = (uint32_t)r0[b0 + c] + r0[b1 + c] + r1[b0 + c] + r1[b1 + c];
+                    float o;
+                    if (x < bulk) o = fmaf((float)sum, s4[c], bias[c]);
+                    else o = (float)sum * s4[c] + bias[c];
+                    dst[c * plane + y * dw + x] = o;
+                }
+            }
+        }
+    }
+}
+
+KO_API int ko_resize_normalize_u8_to_f32_chw_bilinear(const uint8_t* src, size_t sw, size_t sh, float* dst,
+                                                      size_t dw, size_t dh, const float scale[3],
+                                                      const float bias[3], int leaf) {
+    if (sw == 2 * dw && sh == 2 * dh) {  // :181-183
+        fused_2x(src, sw, sh, dst, dw, dh, scale, bias, leaf);
+        return 0;
+    }
+    if (dw == 0 || dh == 0 || sw == 0 || sh == 0) return 0;  // :184-186
+    const float scale_x = (float)sw / (float)dw;
+    const float scale_y = (float)sh / (float)dh;
+    const size_t src_stride = sw * 3;
+    std::vector<size_t> x0b(dw), x1b(dw);
+    std::vector<float> wx(dw);
+    for (size_t dx = 0; dx < dw; ++dx) {  // :196-203
+        float fx = ((float)dx + 0.5f) * scale_x - 0.5f;
+        fx = std::max(fx, 0.0f);
+        const size_t x0 = std::min((size_t)fx, sw - 1);
+        const size_t x1 = std::min(x0 + 1, sw - 1);
+        x0b[dx] = x0 * 3;
+        x1b[dx] = x1 * 3;
+        wx[dx] = fx - (float)x0;
+    }
+    size_t bulk = 0;
+    if (leaf == KO_LEAF_X86_AVX2_FMA) bulk = dw & ~(size_t)7;       // :448
+    if (leaf == KO_LEAF_AARCH64_NEON) bulk = dw & ~(size_t)3;       // :355
+    const size_t plane = dw * dh;
+    const long long nchunks = (long long)((dh + 7) / 8);  // ROWS_PER_TASK = 8 (:209)
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ck = 0; ck < nchunks; ++ck) {
+        const size_t y_end = std::min<size_t>(dh, (size_t)(ck + 1) * 8);
+        for (size_t y = (size_t)ck * 8; y < y_end; ++y) {
+            float fy = ((float)y + 0.5f) * scale_y - 0.5f;
+            fy = std::max(fy, 0.0f);
+            const size_t y0 = std::min((size_t)fy, sh - 1);
+            const size_t y1 = std::min(y0 + 1, sh - 1);
+            const float wy = fy - (float)y0;
+            const uint8_t* row0 = src + y0 * src_stride;
+            const uint8_t* row1 = src + y1 * src_stride;
+            for (size_t dx = 0; dx < dw; ++dx) {
+                const size_t o0 = x0b[dx], o1 = x1b[dx];
+                const float w = wx[dx];
+                for (int c = 0; c < 3; ++c) {
+                    const float a = (float)row0[o0 + c], b = (float)row0[o1 + c];
+                    const float cc = (float)row1[o0 + c], d = (float)row1[o1 + c];
+                    float o;
+                    if (dx < bulk) {  // :475-478  fmadd(sub(b,a), wx, a) …
+                        const float top = fmaf(b - a, w, a);
+                        const float bot = fmaf(d - cc, w, cc);
+                        const float val = fmaf(bot - top, wy, top);
+                        o = fmaf(val, scale[c], bias[c]);
+                    } else {  // :286-317
+                        const float top = a + w * (b - a);
+                        const float bot = cc + w * (d - cc);
+                        const float val = top + wy * (bot - top);
+                        o = val * scale[c] + bias[c];
+                    }
+                    dst[c * plane + y * dw + dx] = o;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a3: u8 bilinear Q14 — resize/bilinear.rs:25-104 (bilinear_tap, axis LUT, row
+// driver), resize/kernels.rs:1141-1166 (bilinear_row_u8_scalar).
+// ─────────────────────────────────────────────────────────────────────────────
+static inline void bilinear_tap(size_t i, double scale, size_t src_len, uint32_t* ofs, uint32_t* fq) {
+    const double s = ((double)i + 0.5) * scale - 0.5;
+    long long i0 = (long long)std::floor(s);
+    double f = s - (double)i0;
+    if (i0 < 0) {
+        i0 = 0;
+        f = 0.0;
+    } else if (i0 >= (long long)src_len - 1) {
+        i0 = (long long)src_len - 2;
+        f = 1.0;
+    }
+    double q = std::round(f * 16384.0);
+    uint32_t fqv = (uint32_t)q;
+    *fq = std::min(fqv, 16384u);
+    *ofs = (uint32_t)i0;
+}
+
+KO_API int ko_resize_bilinear_u8(const uint8_t* src, size_t sw, size_t sh, uint8_t* dst, size_t dw, size_t dh,
+                                 size_t C) {
+    if (!(C == 1 || C == 3 || C == 4)) return -1;
+    if (sw < 2 || sh < 2) return -2;  // resize/mod.rs:318-320
+    const double scale_x = (double)sw / (double)dw, scale_y = (double)sh / (double)dh;
+    std::vector<uint32_t> xofs(dw), xfx(dw), xfx1(dw);
+    for (size_t i = 0; i < dw; ++i) {
+        bilinear_tap(i, scale_x, sw, &xofs[i], &xfx[i]);
+        xfx1[i] = 16384u - xfx[i];
+    }
+    const size_t ss = sw * C, ds = dw * C;
+    const long long nchunks = (long long)((dh + 15) / 16);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ck = 0; ck < nchunks; ++ck) {
+        const size_t y_end = std::min<size_t>(dh, (size_t)(ck + 1) * 16);
+        for (size_t y = (size_t)ck * 16; y < y_end; ++y) {
+            uint32_t yi, fy;
+            bilinear_tap(y, scale_y, sh, &yi, &fy);
+            const uint64_t fy1 = 16384u - fy;
+            const uint8_t* row0 = src + (size_t)yi * ss;
+            const uint8_t* row1 = src + ((size_t)yi + 1) * ss;
+            uint8_t* drow = dst + y * ds;
+            for (size_t x = 0; x < dw; ++x) {
+                const size_t off = (size_t)xofs[x] * C;
+                const uint64_t fx = xfx[x], fx1 = xfx1[x];
+                for (size_t ch = 0; ch < C; ++ch) {
+                    const uint64_t p00 = row0[off + ch], p01 = row0[off + C + ch];
+                    const uint64_t p10 = row1[off + ch], p11 = row1[off + C + ch];
+                    const uint64_t top = p00 * fx1 + p01 * fx;
+                    const uint64_t bot = p10 * fx1 + p11 * fx;
+                    drow[x * C + ch] = (uint8_t)((top * fy1 + bot * (uint64_t)fy + (1ull << 27)) >> 28);
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a4: warp_affine — warp/affine.rs:18-38 (invert), :70-79 (rotation matrix),
+// :123-366 (warp), warp/span.rs:36-81 (valid span).
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API void ko_invert_affine_transform(const float m[6], float out[6]) {
+    const float a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5];
+    const float determinant = a * e - b * d;
+    const float inv_determinant = (determinant != 0.0f) ? 1.0f / determinant : 0.0f;
+    const float new_a = e * inv_determinant;
+    const float new_b = -b * inv_determinant;
+    const float new_d = -d * inv_determinant;
+    const float new_e = a * inv_determinant;
+    const float new_c = -(new_a * c + new_b * f);
+    const float new_f = -(new_d * c + new_e * f);
+    out[0] = new_a; out[1] = new_b; out[2] = new_c; out[3] = new_d; out[4] = new_e; out[5] = new_f;
+}
+
+KO_API void ko_get_rotation_matrix2d(float cx, float cy, float angle_deg, float scale, float out[6]) {
+    const float PI_F = 3.14159265358979323846f;  // std::f32::consts::PI
+    const float angle = angle_deg * PI_F / 180.0f;
+    const float alpha = scale * cosf(angle);
+    const float beta = scale * sinf(angle);
+    const float tx = (1.0f - alpha) * cx - beta * cy;
+    const float ty = beta * cx + (1.0f - alpha) * cy;
+    out[0] = alpha; out[1] = beta; out[2] = tx; out[3] = -beta; out[4] = alpha; out[5] = ty;
+}
+
+static inline void constrain_span(float a, float b, bool ge, float eps, long long* lo, long long* hi) {  // span.rs:36-57
+    if (std::fabs(a) < eps || a == 0.0f) {
+        const bool feasible = ge ? (b >= 0.0f) : (b < 0.0f);
+        if (!feasible) *hi = *lo;
+        return;
+    }
+    const float k = -b / a;
+    auto to_i64 = [](float v) -> long long {  // Rust `as i64` saturates; NaN -> 0
+        if (std::isnan(v)) return 0;
+        if (v >= 9.2233720368547758e18f) return INT64_MAX;
+        if (v <= -9.2233720368547758e18f) return INT64_MIN;
+        return (long long)v;
+    };
+    auto sat_add1 = [](long long v) -> long long { return v == INT64_MAX ? v : v + 1; };
+    if (ge && a > 0.0f) *lo = std::max(*lo, to_i64(std::ceil(k)));
+    else if (ge && !(a > 0.0f)) *hi = std::min(*hi, sat_add1(to_i64(std::floor(k))));
+    else if (!ge && a > 0.0f) *hi = std::min(*hi, to_i64(std::ceil(k)));
+    else *lo = std::max(*lo, sat_add1(to_i64(std::floor(k))));
+}
+
+static inline void affine_valid_span(float d0, float s00, float up0, float d1, float s01, float up1, size_t dst_w,
+                                     float eps, size_t* out_lo, size_t* out_hi) {  // span.rs:62-81
+    long long lo = 0, hi = (long long)dst_w;
+    const float ds[2] = {d0, d1}, ss[2] = {s00, s01}, us[2] = {up0, up1};
+    for (int i = 0; i < 2; ++i) {
+        constrain_span(ds[i], ss[i], true, eps, &lo, &hi);
+        constrain_span(ds[i], ss[i] - us[i], false, eps, &lo, &hi);
+        if (lo >= hi) { *out_lo = 0; *out_hi = 0; return; }
+    }
+    lo = std::min(std::max(lo, 0ll), (long long)dst_w);
+    hi = std::min(std::max(hi, 0ll), (long long)dst_w);
+    if (lo >= hi) { *out_lo = 0; *out_hi = 0; }
+    else { *out_lo = (size_t)lo; *out_hi = (size_t)hi; }
+}
+
+// Exposed for the span unit tests (warp/span.rs:95-138).
+KO_API void ko_constrain_span(float a, float b, int ge, float eps, long long lo_in, long long hi_in, long long* lo,
+                              long long* hi) {
+    *lo = lo_in; *hi = hi_in;
+    constrain_span(a, b, ge != 0, eps, lo, hi);
+}
+KO_API void ko_affine_valid_span(const float axes[6], size_t dst_w, float eps, size_t* lo, size_t* hi) {
+    affine_valid_span(axes[0], axes[1], axes[2], axes[3], axes[4], axes[5], dst_w, eps, lo, hi);
+}
+
+KO_API int ko_warp_affine_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh, size_t C,
+                              const float m[6], int mode) {
+    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;
+    float mi[6];
+    ko_invert_affine_transform(m, mi);
+    const float dsx = mi[0], dsy = mi[3];
+    const float src_w_f = (float)sw, src_h_f = (float)sh;
+    std::vector<float> xstep_x(dw), xstep_y(dw);  // :185-186
+    for (size_t x = 0; x < dw; ++x) { xstep_x[x] = dsx * (float)x; xstep_y[x] = dsy * (float)x; }
+    auto in_bounds = [&](float sx0, float sy0, size_t x) -> bool {  // :201-215
+        bool x_ok, y_ok;
+        if (std::fabs(dsx) < 1e-6f) x_ok = sx0 >= 0.0f && sx0 < src_w_f;
+        else { const float sx = dsx * (float)x + sx0; x_ok = sx >= 0.0f && sx < src_w_f; }
+        if (std::fabs(dsy) < 1e-6f) y_ok = sy0 >= 0.0f && sy0 < src_h_f;
+        else { const float sy = dsy * (float)x + sy0; y_ok = sy >= 0.0f && sy < src_h_f; }
+        return x_ok && y_ok;
+    };
+    const size_t row_len = dw * C;
+    const long long nchunks = (long long)((dh + 15) / 16);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ck = 0; ck < nchunks; ++ck) {
+        const size_t y_end = std::min<size_t>(dh, (size_t)(ck + 1) * 16);
+        for (size_t y = (size_t)ck * 16; y < y_end; ++y) {
+            float* dst_row = dst + y * row_len;
+            const float y_f = (float)y;
+            const float sx0 = mi[1] * y_f + mi[2];
+            const float sy0 = mi[4] * y_f + mi[5];
+            size_t lo, hi;
+            affine_valid_span(dsx, sx0, src_w_f, dsy, sy0, src_h_f, dw, 1e-6f, &lo, &hi);
+            if (lo >= hi) { lo = 0; hi = 0; }
+            else {  // refine_range :216-238
+                while (lo < hi && !in_bounds(sx0, sy0, lo)) ++lo;
+                while (lo > 0 && in_bounds(sx0, sy0, lo - 1)) --lo;
+                while (hi > lo && !in_bounds(sx0, sy0, hi - 1)) --hi;
+                while (hi < dw && in_bounds(sx0, sy0, hi)) ++hi;
+                if (lo >= hi) { lo = 0; hi = 0; }
+            }
+            std::fill(dst_row, dst_row + lo * C, 0.0f);
+            std::fill(dst_row + hi * C, dst_row + row_len, 0.0f);
+            for (size_t x = lo; x < hi; ++x) {
+                const float sx = xstep_x[x] + sx0;
+                const float sy = xstep_y[x] + sy0;
+                float* px = dst_row + x * C;
+                if (mode == KO_NEAREST) {  // :268-272
+                    float rx = roundf(sx), ry = roundf(sy);
+                    rx = std::min(std::max(rx, 0.0f), src_w_f - 1.0f);
+                    ry = std::min(std::max(ry, 0.0f), src_h_f - 1.0f);
+                    const size_t xi = (size_t)rx, yi = (size_t)ry;
+                    for (size_t k = 0; k < C; ++k) px[k] = src[(yi * sw + xi) * C + k];
+                } else {  // :292-317
+                    const float sx_c = std::min(std::max(sx, 0.0f), src_w_f - 1.0f);
+                    const float sy_c = std::min(std::max(sy, 0.0f), src_h_f - 1.0f);
+                    const size_t x0 = (size_t)sx_c, y0 = (size_t)sy_c;
+                    const size_t x1 = std::min(x0 + 1, sw - 1), y1 = std::min(y0 + 1, sh - 1);
+                    const float fx = sx_c - (float)x0, fy = sy_c - (float)y0;
+                    const float w00 = (1.0f - fy) * (1.0f - fx);
+                    const float w10 = (1.0f - fy) * fx;
+                    const float w01 = fy * (1.0f - fx);
+                    const float w11 = fy * fx;
+                    const size_t b00 = (y0 * sw + x0) * C, b10 = (y0 * sw + x1) * C;
+                    const size_t b01 = (y1 * sw + x0) * C, b11 = (y1 * sw + x1) * C;
+                    for (size_t k = 0; k < C; ++k)
+                        px[k] = w00 * src[b00 + k] + w10 * src[b10 + k] + w01 * src[b01 + k] + w11 * src[b11 + k];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a5: warp_perspective — warp/perspective.rs:11-72 (det/adjugate/invert,
+// transform_point), :115-165 (warp).  Out-of-bounds destination pixels are
+// left untouched (CPU semantics); the CUDA twin writes 0, so parity tests
+// zero-initialise dst (cuda/warp_perspective.rs:722-726).
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API int ko_invert_homography(const float m[9], float inv[9]) {
+    const float det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                      m[2] * (m[3] * m[7] - m[4] * m[6]);
+    const float h8_sq = m[8] * m[8];
+    const float FLT_EPS = 1.1920929e-07f;
+    const float det_norm = (h8_sq > FLT_EPS) ? det / (h8_sq * std::fabs(m[8])) : det;
+    if (std::fabs(det_norm) < 1e-10f) return -1;
+    const float adj[9] = {
+        m[4] * m[8] - m[5] * m[7], m[2] * m[7] - m[1] * m[8], m[1] * m[5] - m[2] * m[4],
+        m[5] * m[6] - m[3] * m[8], m[0] * m[8] - m[2] * m[6], m[2] * m[3] - m[0] * m[5],
+        m[3] * m[7] - m[4] * m[6], m[1] * m[6] - m[0] * m[7], m[0] * m[4] - m[1] * m[3]};
+    const float inv_det = 1.0f / det;
+    for (int i = 0; i < 9; ++i) inv[i] = adj[i] * inv_det;
+    return 0;
+}
+
+KO_API int ko_warp_perspective_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh,
+                                   size_t C, const float m[9], int mode) {
+    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;
+    float im[9];
+    if (ko_invert_homography(m, im) != 0) return -2;  // CannotComputeDeterminant
+    const long long nchunks = (long long)((dh + 15) / 16);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long long ck = 0; ck < nchunks; ++ck) {
+        const size_t y_end = std::min<size_t>(dh, (size_t)(ck + 1) * 16);
+        for (size_t r = (size_t)ck * 16; r < y_end; ++r) {
+            for (size_t c = 0; c < dw; ++c) {
+                const float x = (float)c, y = (float)r;
+                const float w = im[6] * x + im[7] * y + im[8];
+                const float xo = (im[0] * x + im[1] * y + im[2]) / w;
+                const float yo = (im[3] * x + im[4] * y + im[5]) / w;
+                if (xo >= 0.0f && xo < (float)sw && yo >= 0.0f && yo < (float)sh) {
+                    float* px = dst + (r * dw + c) * C;
+                    for (size_t k = 0; k < C; ++k)
+                        px[k] = (mode == KO_BILINEAR) ? bilinear_interpolation(src, sh, sw, C, xo, yo, k)
+                                                      : nearest_neighbor_interpolation(src, sh, sw, C, xo, yo, k);
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a6/a7: filters — filter/kernels.rs:25-41 (gaussian taps), :55-72 (sobel
+// taps); filter/separable_filter.rs:87-155 (engine: H into f32 temp, then V;
+// ascending taps; acc += v*k unfused; OOB taps skipped); filter/ops.rs:116-163
+// (gaussian_blur parameter resolution), :174-203 (sobel).
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API void ko_gaussian_kernel_1d(size_t ksize, float sigma, float* out) {
+    const float mean = (float)(ksize - 1) / 2.0f;
+    const float sigma_sq = sigma * sigma;
+    for (size_t i = 0; i < ksize; ++i) {
+        const float x = (float)i - mean;
+        out[i] = expf(-(x * x) / (2.0f * sigma_sq));
+    }
+    float norm = 0.0f;  // iter().sum::<f32>() — sequential, starting from 0.0
+    for (size_t i = 0; i < ksize; ++i) norm += out[i];
+    for (size_t i = 0; i < ksize; ++i) out[i] /= norm;
+}
+
+KO_API int ko_sobel_kernel_1d(size_t ksize, float* kx, float* ky) {
+    if (ksize == 3) {
+        const float a[3] = {-1.0f, 0.0f, 1.0f}, b[3] = {1.0f, 2.0f, 1.0f};
+        std::memcpy(kx, a, sizeof a); std::memcpy(ky, b, sizeof b);
+        return 0;
+    }
+    if (ksize == 5) {
+        const float a[5] = {-1.0f, -2.0f, 0.0f, 2.0f, 1.0f}, b[5] = {1.0f, 4.0f, 6.0f, 4.0f, 1.0f};
+        std::memcpy(kx, a, sizeof a); std::memcpy(ky, b, sizeof b);
+        return 0;
+    }
+    return -1;
+}
+
+// `threads`: 1 = faithful (the reference engine is single-threaded); >1 = row-parallel
+// variant with identical arithmetic (reported separately in the CPU baseline).
+static void separable_filter_impl(const float* src, float* dst, size_t rows, size_t cols, size_t C, const float* kx,
+                                  size_t kxn, const float* ky, size_t kyn, bool mt) {
+    std::vector<float> temp(rows * cols * C, 0.0f);
+    const long long half_x = (long long)(kxn / 2), half_y = (long long)(kyn / 2);
+#pragma omp parallel for schedule(static) if (mt)
+    for (long long r = 0; r < (long long)rows; ++r) {
+        const size_t row_offset = (size_t)r * cols * C;
+        std::vector<float> acc(C);
+        for (size_t c = 0; c < cols; ++c) {
+            std::fill(acc.begin(), acc.end(), 0.0f);
+            for (size_t t = 0; t < kxn; ++t) {
+                const long long x = (long long)c + (long long)t - half_x;
+                if (x >= 0 && x < (long long)cols) {
+                    const size_t idx = row_offset + (size_t)x * C;
+                    for (size_t ch = 0; ch < C; ++ch) acc[ch] += src[idx + ch] * kx[t];
+                }
+            }
+            for (size_t ch = 0; ch < C; ++ch) temp[row_offset + c * C + ch] = acc[ch];
+        }
+    }
+#pragma omp parallel for schedule(static) if (mt)
+    for (long long r = 0; r < (long long)rows; ++r) {
+        const size_t row_offset = (size_t)r * cols * C;
+        std::vector<float> acc(C);
+        for (size_t c = 0; c < cols; ++c) {
+            std::fill(acc.begin(), acc.end(), 0.0f);
+            for (size_t t = 0; t < kyn; ++t) {
+                const long long y = r + (long long)t - half_y;
+                if (y >= 0 && y < (long long)rows) {
+                    const size_t idx = (size_t)y * cols * C + c * C;
+                    for (size_t ch = 0; ch < C; ++ch) acc[ch] += temp[idx + ch] * ky[t];
+                }
+            }
+            for (size_t ch = 0; ch < C; ++ch) dst[row_offset + c * C + ch] = acc[ch];
+        }
+    }
+}
+
+KO_API int ko_separable_filter_f32(const float* src, float* dst, size_t rows, size_t cols, size_t C, const float* kx,
+                                   size_t kxn, const float* ky, size_t kyn, int mt) {
+    if (kxn == 0 || kyn == 0) return -1;  // InvalidKernelLength
+    separable_filter_impl(src, dst, rows, cols, C, kx, kxn, ky, kyn, mt != 0);
+    return 0;
+}
+
+// Resolve gaussian_blur's (kernel_size, sigma) exactly as ops.rs:122-153.  Returns 0 and
+// the resolved values, or -1 (InvalidSigmaValue).
+KO_API int ko_gaussian_resolve(size_t kx_in, size_t ky_in, float sx_in, float sy_in, size_t* kx, size_t* ky,
+                               float* sx, float* sy) {
+    size_t kernel_x = kx_in, kernel_y = ky_in;
+    float sigma_x = sx_in, sigma_y = sy_in;
+    if (sigma_y <= 0.0f) sigma_y = sigma_x;
+    auto auto_k = [](float s) -> size_t {
+        const float v = 2.0f * roundf(4.0f * s) + 1.0f;
+        size_t k = v <= 0.0f ? 0 : (size_t)v;
+        return k | 1;
+    };
+    if (kernel_x == 0 && sigma_x > 0.0f) kernel_x = auto_k(sigma_x);
+    if (kernel_y == 0 && sigma_y > 0.0f) kernel_y = auto_k(sigma_y);
+    if (!(kernel_x > 0 && kernel_x % 2 == 1 && kernel_y > 0 && kernel_y % 2 == 1)) return -1;
+    sigma_x = std::max(sigma_x, 0.0f);
+    sigma_y = std::max(sigma_y, 0.0f);
+    if (sigma_x == 0.0f) sigma_x = ((float)kernel_x - 1.0f) / 8.0f;
+    if (sigma_y == 0.0f) sigma_y = ((float)kernel_y - 1.0f) / 8.0f;
+    *kx = kernel_x; *ky = kernel_y; *sx = sigma_x; *sy = sigma_y;
+    return 0;
+}
+
+KO_API int ko_gaussian_blur_f32(const float* src, float* dst, size_t rows, size_t cols, size_t C, size_t kx_in,
+                                size_t ky_in, float sx_in, float sy_in, int mt) {
+    size_t kxn, kyn;
+    float sx, sy;
+    if (ko_gaussian_resolve(kx_in, ky_in, sx_in, sy_in, &kxn, &kyn, &sx, &sy) != 0) return -1;
+    std::vector<float> kx(kxn), ky(kyn);
+    ko_gaussian_kernel_1d(kxn, sx, kx.data());
+    ko_gaussian_kernel_1d(kyn, sy, ky.data());
+    separable_filter_impl(src, dst, rows, cols, C, kx.data(), kxn, ky.data(), kyn, mt != 0);
+    return 0;
+}
+
+KO_API int ko_sobel_f32(const float* src, float* dst, size_t rows, size_t cols, size_t C, size_t ksize, int mt) {
+    float kx[5], ky[5];
+    if (ko_sobel_kernel_1d(ksize, kx, ky) != 0) return -1;
+    const size_t n = rows * cols * C;
+    std::vector<float> gx(n, 0.0f), gy(n, 0.0f);
+    separable_filter_impl(src, gx.data(), rows, cols, C, kx, ksize, ky, ksize, mt != 0);  // :191-192
+    separable_filter_impl(src, gy.data(), rows, cols, C, ky, ksize, kx, ksize, mt != 0);  // :194-195
+#pragma omp parallel for schedule(static) if (mt != 0)
+    for (long long i = 0; i < (long long)n; ++i) dst[i] = sqrtf(gx[i] * gx[i] + gy[i] * gy[i]);  // :197-200
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a10: normalize — normalize.rs:56-87 (mean/std), :123-146 (find_min_max),
+// :191-222 (min_max), :235-263 + :407-421 (normalize_rgb_u8; AVX2 leaf uses
+// fmadd on the npixels&~7 bulk).
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API void ko_normalize_mean_std_f32(const float* src, float* dst, size_t npixels, size_t C, const float* mean,
+                                      const float* stdv) {
+#pragma omp parallel for schedule(static) if (npixels >= 65536)
+    for (long long i = 0; i < (long long)npixels; ++i)
+        for (size_t c = 0; c < C; ++c) dst[i * C + c] = (src[i * C + c] - mean[c]) / stdv[c];
+}
+
+KO_API int ko_find_min_max_f32(const float* src, size_t n, float* mn, float* mx) {
+    if (n == 0) return -1;
+    float lo = src[0], hi = src[0];
+    for (size_t i = 0; i < n; ++i) {
+        if (src[i] < lo) lo = src[i];
+        if (src[i] > hi) hi = src[i];
+    }
+    *mn = lo; *mx = hi;
+    return 0;
+}
+
+KO_API int ko_normalize_min_max_f32(const float* src, float* dst, size_t n, float mn, float mx) {
+    float min_val, max_val;
+    if (ko_find_min_max_f32(src, n, &min_val, &max_val) != 0) return -1;
+#pragma omp parallel for schedule(static) if (n >= 65536)
+    for (long long i = 0; i < (long long)n; ++i)
+        dst[i] = (src[i] - min_val) * (mx - mn) / (max_val - min_val) + mn;
+    return 0;
+}
+
+KO_API void ko_normalize_rgb_u8(const uint8_t* src, float* dst, size_t npixels, const float scale[3],
+                                const float offset[3], int leaf) {
+    size_t bulk = 0;
+    if (leaf == KO_LEAF_X86_AVX2_FMA || leaf == KO_LEAF_AARCH64_NEON) bulk = npixels & ~(size_t)7;
+#pragma omp parallel for schedule(static) if (npixels >= 1024 * 1024)
+    for (long long i = 0; i < (long long)npixels; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const float v = (float)src[i * 3 + c];
+            dst[i * 3 + c] = ((size_t)i < bulk) ? fmaf(v, scale[c], offset[c]) : v * scale[c] + offset[c];
+        }
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a11: std_mean — core.rs:42-67.  f64 accumulation of integer-valued terms is
+// exact below 2^53, so integer sums reproduce it.  Returns raw sums too.
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API void ko_std_mean_u8_c3(const uint8_t* src, size_t npixels, double stdv[3], double mean[3],
+                              uint64_t sums[6]) {
+    double sum[3] = {0, 0, 0}, sq[3] = {0, 0, 0};
+    for (size_t i = 0; i < npixels; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const double p = (double)src[i * 3 + c];
+            sum[c] += p;
+            sq[c] += p * p;  // powi(2)
+        }
+    const double n = (double)npixels;
+    for (int c = 0; c < 3; ++c) {
+        mean[c] = sum[c] / n;
+        stdv[c] = std::sqrt(sq[c] / n - mean[c] * mean[c]);
+        if (sums) { sums[c] = (uint64_t)sum[c]; sums[3 + c] = (uint64_t)sq[c]; }
+    }
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
+// a12: camera preprocess.  The NV12/YUYV path has NO CPU implementation in the
+// reference; the CUDA source string preprocess.rs:430-647 is the spec, restated
+// here op for op (compiled there with fmad=false, IEEE div).  Affine::new
+// preprocess.rs:349-370.
+// ─────────────────────────────────────────────────────────────────────────────
+struct ko_preprocess_desc {
+    float scale_x, scale_y, pad_x, pad_y;
+    int32_t src_w, src_h, src_pitch, src_bpp, fmt;  // fmt: 0 RGB-order, 1 BGR-order, 2 gray, 3 NV12, 4 YUYV
+    int32_t dst_w, dst_h;
+    float mean[3], inv_std[3];
+    float pad_value;
+    int32_t sampling;  // 0 nearest, 1 bilinear
+};
+
+enum { KO_RESIZE_LETTERBOX = 0, KO_RESIZE_STRETCH = 1 };
+
+KO_API void ko_preprocess_affine(int mode, size_t sw, size_t sh, size_t dw, size_t dh, float out[4]) {
+    if (mode == KO_RESIZE_LETTERBOX) {
+        const float s = std::min((float)dw / (float)sw, (float)dh / (float)sh);
+        out[0] = s; out[1] = s;
+        out[2] = ((float)dw - (float)sw * s) * 0.5f;
+        out[3] = ((float)dh - (float)sh * s) * 0.5f;
+    } else {
+        out[0] = (float)dw / (float)sw; out[1] = (float)dh / (float)sh; out[2] = 0.0f; out[3] = 0.0f;
+    }
+}
+
+static inline void yuv_to_rgbf(int yv, int u, int v, float px[3]) {  // :501-508
+    const int yy = std::max(yv - 16, 0) * 1220542;
+    u -= 128; v -= 128;
+    px[2] = (float)std::min(std::max((yy + 2116026 * u + (1 << 19)) >> 20, 0), 255);
+    px[1] = (float)std::min(std::max((yy + (-409993) * u + (-852492) * v + (1 << 19)) >> 20, 0), 255);
+    px[0] = (float)std::min(std::max((yy + 1673527 * v + (1 << 19)) >> 20, 0), 255);
+}
+
+static inline void fetch_px(const uint8_t* src, int x, int y, const ko_preprocess_desc& d, float px[3]) {  // :510-530
+    if (d.fmt <= 1) {
+        const uint8_t* p = src + (long long)y * d.src_pitch + x * d.src_bpp;
+        if (d.fmt == 0) { px[0] = (float)p[0]; px[1] = (float)p[1]; px[2] = (float)p[2]; }
+        else { px[0] = (float)p[2]; px[1] = (float)p[1]; px[2] = (float)p[0]; }
+    } else if (d.fmt == 2) {
+        const float v = (float)src[(long long)y * d.src_pitch + x];
+        px[0] = v; px[1] = v; px[2] = v;
+    } else if (d.fmt == 3) {
+        const int yv = src[(long long)y * d.src_w + x];
+        const uint8_t* uv = src + (long long)d.src_w * d.src_h + (long long)(y >> 1) * d.src_w + (x >> 1) * 2;
+        yuv_to_rgbf(yv, uv[0], uv[1], px);
+    } else {
+        const uint8_t* grp = src + (long long)y * d.src_pitch + (x >> 1) * 4;
+        const int yv = grp[(x & 1) ? 2 : 0];
+        yuv_to_rgbf(yv, grp[1], grp[3], px);
+    }
+}
+
+// f32 -> binary16 bits, RNE — preprocess.rs:461-484 (f2h).
+KO_API uint16_t ko_f2h(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    const int exp = (int)((x >> 23) & 0xFFu) - 127 + 15;
+    uint32_t man = x & 0x7FFFFFu;
+    if (exp >= 31) {
+        // Mirrors the reference exactly: any nonzero mantissa sets the quiet bit, also for a
+        // FINITE f32 that overflows binary16 (the reference's own rule, preprocess.rs:467-471).
+        const uint32_t nan_bit = (man != 0u) ? 0x0200u : 0u;
+        return (uint16_t)(sign | 0x7C00u | nan_bit);
+    }
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;
+        man |= 0x800000u;
+        const uint32_t shift = (uint32_t)(14 - exp);
+        uint16_t h = (uint16_t)(sign | (man >> shift));
+        const uint32_t rem = man & ((1u << shift) - 1u);
+        const uint32_t mid = 1u << (shift - 1u);
+        if (rem > mid || (rem == mid && (h & 1u))) h++;
+        return h;
+    }
+    uint16_t h = (uint16_t)(sign | ((uint32_t)exp << 10) | (man >> 13));
+    const uint32_t rem = man & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+    return h;
+}
+
+// One frame.  out_f16 != 0 -> dst is uint16_t (binary16 bits).  If `touched` is non-null
+// (src-buffer-sized byte mask) every source byte addressed by a tap is marked — used to
+// count the algorithmic bytes of SURVEY §8(d) exactly.
+KO_API int ko_preprocess_frame(const uint8_t* src, void* dst, const ko_preprocess_desc* dp, int out_f16,
+                               uint8_t* touched) {
+    const ko_preprocess_desc d = *dp;
+    if (d.sampling != KO_NEAREST && d.sampling != KO_BILINEAR) return -1;
+    const int pixels = d.dst_w * d.dst_h;
+    float* dst32 = (float*)dst;
+    uint16_t* dst16 = (uint16_t*)dst;
+    auto mark = [&](int x, int y) {
+        if (!touched) return;
+        if (d.fmt <= 1) { for (int c = 0; c < 3; ++c) touched[(long long)y * d.src_pitch + x * d.src_bpp + c] = 1; }
+        else if (d.fmt == 2) touched[(long long)y * d.src_pitch + x] = 1;
+        else if (d.fmt == 3) {
+            touched[(long long)y * d.src_w + x] = 1;
+            const long long o = (long long)d.src_w * d.src_h + (long long)(y >> 1) * d.src_w + (x >> 1) * 2;
+            touched[o] = 1; touched[o + 1] = 1;
+        } else {
+            const long long o = (long long)y * d.src_pitch + (x >> 1) * 4;
+            touched[o + ((x & 1) ? 2 : 0)] = 1; touched[o + 1] = 1; touched[o + 3] = 1;
+        }
+    };
+#pragma omp parallel for schedule(static) if (pixels >= 65536 && !touched)
+    for (int i = 0; i < pixels; ++i) {
+        const int ox = i % d.dst_w, oy = i / d.dst_w;
+        const float sx = ((float)ox - d.pad_x) / d.scale_x;  // plan_pixel :437-448
+        const float sy = ((float)oy - d.pad_y) / d.scale_y;
+        const bool inside = !(sx < 0.0f || sy < 0.0f || sx >= (float)d.src_w || sy >= (float)d.src_h);
+        float px[3];
+        if (inside) {
+            if (d.sampling == KO_BILINEAR) {  // :534-554
+                int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+                const float ax = sx - (float)x0, ay = sy - (float)y0;
+                const int x1 = std::min(x0 + 1, d.src_w - 1), y1 = std::min(y0 + 1, d.src_h - 1);
+                x0 = std::max(x0, 0); y0 = std::max(y0, 0);
+                float t00[3], t10[3], t01[3], t11[3];
+                fetch_px(src, x0, y0, d, t00); fetch_px(src, x1, y0, d, t10);
+                fetch_px(src, x0, y1, d, t01); fetch_px(src, x1, y1, d, t11);
+                mark(x0, y0); mark(x1, y0); mark(x0, y1); mark(x1, y1);
+                for (int c = 0; c < 3; ++c) {
+                    const float top = t00[c] + (t10[c] - t00[c]) * ax;
+                    const float bot = t01[c] + (t11[c] - t01[c]) * ax;
+                    px[c] = top + (bot - top) * ay;
+                }
+            } else {  // :556-563
+                const int xn = std::min(std::max((int)roundf(sx), 0), d.src_w - 1);
+                const int yn = std::min(std::max((int)roundf(sy), 0), d.src_h - 1);
+                fetch_px(src, xn, yn, d, px);
+                mark(xn, yn);
+            }
+        } else {
+            px[0] = px[1] = px[2] = d.pad_value;
+        }
+        const float o0 = (px[0] / 255.0f - d.mean[0]) * d.inv_std[0];  // BODY :610-612
+        const float o1 = (px[1] / 255.0f - d.mean[1]) * d.inv_std[1];
+        const float o2 = (px[2] / 255.0f - d.mean[2]) * d.inv_std[2];
+        if (out_f16) { dst16[i] = ko_f2h(o0); dst16[pixels + i] = ko_f2h(o1); dst16[2 * pixels + i] = ko_f2h(o2); }
+        else { dst32[i] = o0; dst32[pixels + i] = o1; dst32[2 * pixels + i] = o2; }
+    }
+    return 0;
+}
+
+// Preprocessor::run_cpu for C==3 RGB + bilinear (preprocess.rs:933-1020): the host path —
+// fused bilinear into the (integer) content box, pad fill, row placement.
+KO_API int ko_preprocess_cpu_rgb_bilinear(const uint8_t* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh,
+                                          int mode, const float mean[3], const float inv_std[3], float pad_value,
+                                          int leaf) {
+    float a[4];
+    ko_preprocess_affine(mode, sw, sh, dw, dh, a);
+    float scale[3], bias[3], pad[3];
+    for (int c = 0; c < 3; ++c) {
+        scale[c] = inv_std[c] / 255.0f;
+        bias[c] = -mean[c] * inv_std[c];
+        pad[c] = pad_value * scale[c] + bias[c];
+    }
+    size_t cw = dw, ch = dh;
+    if (mode == KO_RESIZE_LETTERBOX) {
+        cw = std::min(std::max((size_t)roundf((float)sw * a[0]), (size_t)1), dw);
+        ch = std::min(std::max((size_t)roundf((float)sh * a[1]), (size_t)1), dh);
+    }
+    const size_t px0 = (dw - cw) / 2, py0 = (dh - ch) / 2;
+    const bool padded = px0 != 0 || py0 != 0 || cw != dw || ch != dh;
+    if (!padded) return ko_resize_normalize_u8_to_f32_chw_bilinear(src, sw, sh, dst, dw, dh, scale, bias, leaf);
+    std::vector<float> content(3 * ch * cw);
+    ko_resize_normalize_u8_to_f32_chw_bilinear(src, sw, sh, content.data(), cw, ch, scale, bias, leaf);
+    const size_t pixels = dw * dh;
+    for (int c = 0; c < 3; ++c) {
+        float* plane = dst + c * pixels;
+        std::fill(plane, plane + pixels, pad[c]);
+        for (size_t y = 0; y < ch; ++y)
+            std::memcpy(plane + (py0 + y) * dw + px0, content.data() + c * ch * cw + y * cw, cw * sizeof(float));
+    }
+    return 0;
+}
+
+// Count distinct source elements addressed by ≥1 tap for the generic bilinear samplers —
+// used only to state algorithmic bytes.  kind: 0 = resize a1 (half-pixel,
+// clamped), 1 = fused a2.
+KO_API size_t ko_count_touched_resize(size_t sw, size_t sh, size_t dw, size_t dh, int kind) {
+    std::vector<uint8_t> tx(sw, 0), ty(sh, 0);
+    auto axis = [&](size_t s, size_t d, std::vector<uint8_t>& t) {
+        for (size_t i = 0; i < d; ++i) {
+            size_t i0, i1;
+            if (kind == 0) {
+                const float a = (float)s / (float)d, b = 0.5f * a - 0.5f;
+                float v = a * (float)i + b;
+                v = std::min(std::max(v, 0.0f), (float)(s - 1));
+                i0 = (size_t)v; i1 = std::min(i0 + 1, s - 1);
+            } else {
+                float f = ((float)i + 0.5f) * ((float)s / (float)d) - 0.5f;
+                f = std::max(f, 0.0f);
+                i0 = std::min((size_t)f, s - 1); i1 = std::min(i0 + 1, s - 1);
+            }
+            t[i0] = 1; t[i1] = 1;
+        }
+    };
+    axis(sw, dw, tx); axis(sh, dh, ty);
+    size_t nx = 0, ny = 0;
+    for (auto v : tx) nx += v;
+    for (auto v : ty) ny += v;
+    return nx * ny;
+}
