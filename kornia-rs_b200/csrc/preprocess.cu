@@ -1,0 +1,240 @@
+// preprocess.cu — the fused camera preprocess (a12; BASELINE config 3): raw frame (RGB/BGR/RGBA/
+// Gray/NV12/YUYV, tight or pitched) → letterbox/stretch resample → (v/255 - mean) * inv_std →
+// planar CHW f32 or f16, for a whole batch in ONE launch.
+//
+// Reference: preprocess.rs:430-647 (the CUDA source string — the specification of this path; there
+// is no CPU implementation for the camera formats), launch seam :1324-1372, batch loop :1277-1280
+// (one launch per frame), Affine::new :349-370.
+//
+// Arithmetic is the reference's, op for op (it JIT-compiles with fmad=false, IEEE division):
+//   sx = ((float)ox - pad_x) / scale_x                         plan_pixel :437-448
+//   bilinear taps x0=floor(sx), x1=min(x0+1,W-1), x0=max(x0,0); decode-in-tap (Q20 → float 0..255)
+//   top = t00 + (t10 - t00)*ax ; px = top + (bot - top)*ay     sample_bilinear :534-554
+//   o = (px / 255.0f - mean) * inv_std                         BODY :610-612
+// One exact shortcut: when ax == 0 the x1 taps are multiplied by zero — `t00 + (t10-t00)*0` is t00
+// bit-for-bit for the finite decoded values — so those taps are not fetched (same for ay == 0).  At
+// integer scales (1080p NV12 → 1080p CHW, config 3a) that removes 3 of the 4 decodes per pixel.
+#include "kb200_common.cuh"
+
+namespace kb200 {
+
+struct PreFrames {
+    const uint8_t* base;  // strided mode
+    size_t stride;
+    const uint8_t* ptr[256];  // pointer-table mode
+};
+
+// preprocess.rs:461-484 — manual RNE f32 -> binary16 (kept bit-identical, including its rule that
+// any exp >= 31 input with a nonzero mantissa gets the quiet bit).
+__device__ __forceinline__ unsigned short f2h_ref(float f) {
+    const unsigned int x = __float_as_uint(f);
+    const unsigned int sign = (x >> 16) & 0x8000u;
+    const int exp = (int)((x >> 23) & 0xFFu) - 127 + 15;
+    unsigned int man = x & 0x7FFFFFu;
+    if (exp >= 31) {
+        const unsigned int nan_bit = (man != 0u) ? 0x0200u : 0u;
+        return (unsigned short)(sign | 0x7C00u | nan_bit);
+    }
+    if (exp <= 0) {
+        if (exp < -10) return (unsigned short)sign;
+        man |= 0x800000u;
+        const unsigned int shift = (unsigned int)(14 - exp);
+        unsigned short h = (unsigned short)(sign | (man >> shift));
+        const unsigned int rem = man & ((1u << shift) - 1u);
+        const unsigned int mid = 1u << (shift - 1u);
+        if (rem > mid || (rem == mid && (h & 1u))) h++;
+        return h;
+    }
+    unsigned short h = (unsigned short)(sign | ((unsigned int)exp << 10) | (man >> 13));
+    const unsigned int rem = man & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;
+    return h;
+}
+
+__device__ __forceinline__ void yuv_to_rgbf(int yv, int u, int v, float px[3]) {  // :501-508
+    const ChromaTerms t = chroma_terms(u, v);
+    int r, g, b;
+    decode_rgb(yy_term(yv), t, r, g, b);
+    px[0] = (float)r; px[1] = (float)g; px[2] = (float)b;
+}
+
+__device__ __forceinline__ void fetch_px(const uint8_t* __restrict__ src, int x, int y, const kb200_preprocess_desc& d,
+                                         float px[3]) {  // :510-530
+    if (d.fmt <= 1) {
+        const uint8_t* p = src + (long long)y * d.src_pitch + x * d.src_bpp;
+        if (d.fmt == 0) { px[0] = (float)p[0]; px[1] = (float)p[1]; px[2] = (float)p[2]; }
+        else { px[0] = (float)p[2]; px[1] = (float)p[1]; px[2] = (float)p[0]; }
+    } else if (d.fmt == 2) {
+        const float v = (float)src[(long long)y * d.src_pitch + x];
+        px[0] = v; px[1] = v; px[2] = v;
+    } else if (d.fmt == 3) {
+        const int yv = src[(long long)y * d.src_w + x];
+        const uint8_t* uv = src + (long long)d.src_w * d.src_h + (long long)(y >> 1) * d.src_w + (x >> 1) * 2;
+        yuv_to_rgbf(yv, uv[0], uv[1], px);
+    } else {
+        const uint8_t* grp = src + (long long)y * d.src_pitch + (x >> 1) * 4;
+        const int yv = grp[(x & 1) ? 2 : 0];
+        yuv_to_rgbf(yv, grp[1], grp[3], px);
+    }
+}
+
+template <bool F16, bool BILINEAR, bool PTRS>
+__global__ void __launch_bounds__(256) preprocess_generic_kernel(const __grid_constant__ kb200_preprocess_desc d,
+                                                                 const __grid_constant__ PreFrames fr, void* __restrict__ dst,
+                                                                 uint32_t frame0) {
+    const int pixels = d.dst_w * d.dst_h;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pixels) return;
+    const uint32_t f = blockIdx.y;
+    const uint8_t* src = PTRS ? fr.ptr[f] : fr.base + (size_t)(frame0 + f) * fr.stride;
+    const int ox = i % d.dst_w, oy = i / d.dst_w;
+    const float sx = __fdiv_rn((float)ox - d.pad_x, d.scale_x);
+    const float sy = __fdiv_rn((float)oy - d.pad_y, d.scale_y);
+    const bool inside = !(sx < 0.0f || sy < 0.0f || sx >= (float)d.src_w || sy >= (float)d.src_h);
+    float px[3];
+    if (inside) {
+        if (BILINEAR) {
+            int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+            const float ax = sx - (float)x0, ay = sy - (float)y0;
+            const int x1 = min(x0 + 1, d.src_w - 1), y1 = min(y0 + 1, d.src_h - 1);
+            x0 = max(x0, 0); y0 = max(y0, 0);
+            float t00[3], t10[3], t01[3], t11[3];
+            fetch_px(src, x0, y0, d, t00);
+            const bool need_x = ax != 0.0f, need_y = ay != 0.0f;
+            if (need_x) fetch_px(src, x1, y0, d, t10);
+            if (need_y) {
+                fetch_px(src, x0, y1, d, t01);
+                if (need_x) fetch_px(src, x1, y1, d, t11);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float top = need_x ? t00[c] + (t10[c] - t00[c]) * ax : t00[c];
+                if (need_y) {
+                    const float bot = need_x ? t01[c] + (t11[c] - t01[c]) * ax : t01[c];
+                    px[c] = top + (bot - top) * ay;
+                } else {
+                    px[c] = top;
+                }
+            }
+        } else {
+            const int xn = min(max((int)roundf(sx), 0), d.src_w - 1);
+            const int yn = min(max((int)roundf(sy), 0), d.src_h - 1);
+            fetch_px(src, xn, yn, d, px);
+        }
+    } else {
+        px[0] = d.pad_value; px[1] = d.pad_value; px[2] = d.pad_value;
+    }
+    const float o0 = (__fdiv_rn(px[0], 255.0f) - d.mean[0]) * d.inv_std[0];
+    const float o1 = (__fdiv_rn(px[1], 255.0f) - d.mean[1]) * d.inv_std[1];
+    const float o2 = (__fdiv_rn(px[2], 255.0f) - d.mean[2]) * d.inv_std[2];
+    const size_t out = (size_t)(frame0 + f) * 3 * pixels + i;
+    if (F16) {
+        unsigned short* o = reinterpret_cast<unsigned short*>(dst);
+        o[out] = f2h_ref(o0); o[out + pixels] = f2h_ref(o1); o[out + 2 * (size_t)pixels] = f2h_ref(o2);
+    } else {
+        float* o = reinterpret_cast<float*>(dst);
+        o[out] = o0; o[out + pixels] = o1; o[out + 2 * (size_t)pixels] = o2;
+    }
+}
+
+static size_t src_bytes(const kb200_preprocess_desc& d) {
+    const size_t chroma = d.fmt == KB200_FMT_NV12 ? (size_t)d.src_w * d.src_h / 2 : 0;
+    return (size_t)d.src_pitch * d.src_h + chroma;
+}
+
+static int validate_desc(const kb200_preprocess_desc* dp) {
+    if (!dp) return fail(KB200_ERR_INVALID_ARGUMENT, "null preprocess descriptor");
+    const kb200_preprocess_desc& d = *dp;
+    if (d.src_w <= 0 || d.src_h <= 0 || d.dst_w <= 0 || d.dst_h <= 0)
+        return fail(KB200_ERR_INVALID_ARGUMENT, "image dimensions must be non-zero");
+    if ((long long)d.dst_w * d.dst_h > 0x7FFFFFFFll) return fail(KB200_ERR_DIMS_TOO_LARGE, "dimensions exceed the 32-bit CUDA kernel index limit");  // :1336-1339
+    if (d.fmt < 0 || d.fmt > 4) return fail(KB200_ERR_INVALID_ARGUMENT, "unknown source format code %d", d.fmt);
+    if (d.sampling != KB200_INTERP_NEAREST && d.sampling != KB200_INTERP_BILINEAR)
+        return fail(KB200_ERR_UNSUPPORTED, "unsupported sampling mode %d (expected Nearest or Bilinear)", d.sampling);
+    if (d.fmt <= 1 && d.src_bpp != 3 && d.src_bpp != 4) return fail(KB200_ERR_UNSUPPORTED, "unsupported source channel count %d (expected 3 or 4)", d.src_bpp);
+    // SourceFormat::dims_ok :188-195 ; pitch covers a row (PitchedSurface::validate :829-842)
+    if (d.fmt == KB200_FMT_NV12 && ((d.src_w | d.src_h) & 1)) return fail(KB200_ERR_INVALID_SOURCE, "invalid raw source for Nv12 at %dx%d (even dimensions required)", d.src_w, d.src_h);
+    if (d.fmt == KB200_FMT_YUYV && (d.src_w & 1)) return fail(KB200_ERR_INVALID_SOURCE, "invalid raw source for Yuyv at %dx%d (even width required)", d.src_w, d.src_h);
+    const int bpp = d.fmt <= 1 ? d.src_bpp : (d.fmt == KB200_FMT_YUYV ? 2 : 1);
+    if ((long long)d.src_pitch < (long long)d.src_w * bpp) return fail(KB200_ERR_INVALID_SOURCE, "invalid pitched surface (need pitch >= width*channels and len >= pitch*height)");
+    if (d.fmt == KB200_FMT_NV12 && d.src_pitch != d.src_w) return fail(KB200_ERR_INVALID_SOURCE, "NV12 frames must be tightly packed (pitch == width)");
+    if (!(d.scale_x > 0.0f) || !(d.scale_y > 0.0f)) return fail(KB200_ERR_INVALID_ARGUMENT, "scale must be positive");
+    return KB200_OK;
+}
+
+template <bool F16>
+static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, const uint8_t* const* frames,
+                             const uint8_t* base, size_t stride, uint32_t batch, void* dst) {
+    const int pixels = d.dst_w * d.dst_h;
+    const bool bil = d.sampling == KB200_INTERP_BILINEAR;
+    for (uint32_t f0 = 0; f0 < batch; f0 += 256) {
+        const uint32_t nb = std::min<uint32_t>(256, batch - f0);
+        PreFrames fr{};
+        fr.base = base; fr.stride = stride;
+        if (frames) for (uint32_t k = 0; k < nb; ++k) fr.ptr[k] = frames[f0 + k];
+        dim3 grid(div_up(pixels, 256), nb);
+        if (frames) {
+            if (bil) preprocess_generic_kernel<F16, true, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            else preprocess_generic_kernel<F16, false, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+        } else {
+            if (bil) preprocess_generic_kernel<F16, true, false><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            else preprocess_generic_kernel<F16, false, false><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+        }
+        KB200_TRY(check_launch("preprocess_generic_kernel"));
+    }
+    return KB200_OK;
+}
+
+template <bool F16>
+static int preprocess_entry(kb200_stream_t stream, const kb200_preprocess_desc* desc, const uint8_t* const* frames,
+                            const size_t* frame_len, const uint8_t* base, size_t base_len, size_t stride,
+                            uint32_t batch, void* dst, size_t dst_len) {
+    KB200_TRY(validate_desc(desc));
+    KB200_TRY(check_ptr("dst", dst));
+    if (batch == 0) return fail(KB200_ERR_INVALID_ARGUMENT, "batch must be non-zero");
+    const size_t need = src_bytes(*desc);
+    if (frames) {
+        for (uint32_t i = 0; i < batch; ++i) {
+            if (!frames[i]) return fail(KB200_ERR_INVALID_ARGUMENT, "null frame pointer at index %u", i);
+            if (frame_len && frame_len[i] < need)  // InvalidRawSource{got,need}, preprocess.rs:1287-1300
+                return fail(KB200_ERR_INVALID_SOURCE, "invalid raw source at %dx%d (got %zu bytes, need %zu)", desc->src_w, desc->src_h, frame_len[i], need);
+        }
+    } else {
+        KB200_TRY(check_ptr("base", base));
+        if (stride < need && batch > 1) return fail(KB200_ERR_INVALID_SOURCE, "frame stride %zu smaller than a frame (%zu bytes)", stride, need);
+        if (base_len < (size_t)(batch - 1) * stride + need)
+            return fail(KB200_ERR_INVALID_SOURCE, "invalid raw source at %dx%d (got %zu bytes, need %zu)", desc->src_w, desc->src_h, base_len, (size_t)(batch - 1) * stride + need);
+    }
+    // BatchMismatch / BadOutputShape: dst must hold [batch,3,H,W]
+    KB200_TRY(check_slice("dst", dst_len, (size_t)batch * 3 * desc->dst_w * desc->dst_h));
+    return launch_preprocess<F16>(as_stream(stream), *desc, frames, base, stride, batch, dst);
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+extern "C" {
+
+KB200_API size_t kb200_preprocess_src_bytes(const kb200_preprocess_desc* desc) { return desc ? src_bytes(*desc) : 0; }
+
+KB200_API int kb200_preprocess_f32(kb200_stream_t stream, const kb200_preprocess_desc* desc, const uint8_t* const* frames,
+                                   const size_t* frame_len, uint32_t batch, float* dst, size_t dst_len) {
+    if (!frames) return fail(KB200_ERR_INVALID_ARGUMENT, "null pointer for 'frames'");
+    return preprocess_entry<false>(stream, desc, frames, frame_len, nullptr, 0, 0, batch, dst, dst_len);
+}
+KB200_API int kb200_preprocess_f16(kb200_stream_t stream, const kb200_preprocess_desc* desc, const uint8_t* const* frames,
+                                   const size_t* frame_len, uint32_t batch, uint16_t* dst, size_t dst_len) {
+    if (!frames) return fail(KB200_ERR_INVALID_ARGUMENT, "null pointer for 'frames'");
+    return preprocess_entry<true>(stream, desc, frames, frame_len, nullptr, 0, 0, batch, dst, dst_len);
+}
+KB200_API int kb200_preprocess_strided_f32(kb200_stream_t stream, const kb200_preprocess_desc* desc, const uint8_t* base,
+                                           size_t base_len, size_t frame_stride, uint32_t batch, float* dst, size_t dst_len) {
+    return preprocess_entry<false>(stream, desc, nullptr, nullptr, base, base_len, frame_stride, batch, dst, dst_len);
+}
+KB200_API int kb200_preprocess_strided_f16(kb200_stream_t stream, const kb200_preprocess_desc* desc, const uint8_t* base,
+                                           size_t base_len, size_t frame_stride, uint32_t batch, uint16_t* dst, size_t dst_len) {
+    return preprocess_entry<true>(stream, desc, nullptr, nullptr, base, base_len, frame_stride, batch, dst, dst_len);
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// resize.cu — f32 HWC bilinear / nearest resize (a1) and the u8 Q14 bilinear resize (a3).
+//
+// Reference: resize/mod.rs:114-207 (CPU `resize`), interpolation/bilinear.rs:16-66,
+// interpolation/nearest.rs:15-30, cuda/resize.rs:97-235 (GPU twins), resize/bilinear.rs:25-104 +
+// resize/kernels.rs:1141-1166 (u8 Q14).
+//
+// Bit-exactness contract (cuda/resize.rs:113-118): the coordinate is `a*x + b` evaluated as an
+// unfused multiply-add, weights are formed first and the four terms summed left to right.  This
+// file is compiled with -fmad=false, so plain `*` and `+` already round twice.
+//
+// B200 design (round 1): thread-per-destination-pixel gather with batch as grid.z; source rows are
+// read through the read-only path (the 2x2 taps of neighbouring threads share sectors, L1 absorbs
+// the reuse), destination rows are written fully coalesced (a warp covers 32 consecutive pixels =
+// 384 contiguous bytes).  The TMA row-span staged variant for the u8→f32 CHW headline path lives in
+// resize_fused.cu.
+#include "kb200_common.cuh"
+
+namespace kb200 {
+
+struct AxisMap {
+    float ax, bx, ay, by;
+};
+
+// PixelMapping::coeffs — cuda/resize.rs:462-478
+static inline void mapping_coeffs(int mapping, uint32_t src_len, uint32_t dst_len, float* a, float* b) {
+    if (mapping == KB200_MAP_HALF_PIXEL) {
+        *a = (float)src_len / (float)dst_len;
+        *b = 0.5f * *a - 0.5f;
+    } else {
+        if (dst_len > 1) { *a = (float)(src_len - 1) / (float)(dst_len - 1); *b = 0.0f; }
+        else { *a = 0.0f; *b = 0.0f; }
+    }
+}
+
+// MODE: 0 nearest, 1 bilinear, 2 bilinear + (v - mean) * inv_std        (cuda/resize.rs:97-235)
+template <int MODE>
+__global__ void __launch_bounds__(256) resize_f32_c3_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                            uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, AxisMap m,
+                                                            float mean0, float mean1, float mean2, float is0, float is1,
+                                                            float is2) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const float* s = src + (size_t)blockIdx.z * sw * sh * 3;
+    float* d = dst + ((size_t)blockIdx.z * dw * dh + (size_t)y * dw + x) * 3;
+    if (MODE == 0) {
+        const uint32_t xi = min((uint32_t)((m.ax * (float)x + m.bx) + 0.5f), sw - 1u);
+        const uint32_t yi = min((uint32_t)((m.ay * (float)y + m.by) + 0.5f), sh - 1u);
+        const float* p = s + ((size_t)yi * sw + xi) * 3;
+        d[0] = __ldg(p); d[1] = __ldg(p + 1); d[2] = __ldg(p + 2);
+        return;
+    }
+    const float sx = fmaxf(fminf(m.ax * (float)x + m.bx, (float)(sw - 1u)), 0.0f);
+    const float sy = fmaxf(fminf(m.ay * (float)y + m.by, (float)(sh - 1u)), 0.0f);
+    const uint32_t x0 = (uint32_t)sx, y0 = (uint32_t)sy;
+    const uint32_t x1 = min(x0 + 1u, sw - 1u), y1 = min(y0 + 1u, sh - 1u);
+    const float fx = sx - (float)x0, fy = sy - (float)y0;
+    const float w00 = (1.0f - fy) * (1.0f - fx);
+    const float w10 = (1.0f - fy) * fx;
+    const float w01 = fy * (1.0f - fx);
+    const float w11 = fy * fx;
+    const float* p00 = s + ((size_t)y0 * sw + x0) * 3;
+    const float* p10 = s + ((size_t)y0 * sw + x1) * 3;
+    const float* p01 = s + ((size_t)y1 * sw + x0) * 3;
+    const float* p11 = s + ((size_t)y1 * sw + x1) * 3;
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = w00 * __ldg(p00 + k) + w10 * __ldg(p10 + k) + w01 * __ldg(p01 + k) + w11 * __ldg(p11 + k);
+    if (MODE == 2) {
+        c[0] = (c[0] - mean0) * is0; c[1] = (c[1] - mean1) * is1; c[2] = (c[2] - mean2) * is2;
+    }
+    d[0] = c[0]; d[1] = c[1]; d[2] = c[2];
+}
+
+// Generic channel count, CPU `resize<C>` semantics (val00 replicate, round() for nearest).
+__global__ void __launch_bounds__(256) resize_f32_generic_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                 uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh,
+                                                                 uint32_t C, AxisMap m, int bilinear) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const float* s = src + (size_t)blockIdx.z * sw * sh * C;
+    float* d = dst + ((size_t)blockIdx.z * dw * dh + (size_t)y * dw + x) * C;
+    // axis_lut: (a*i + b).clamp(0, max)   resize/mod.rs:169-176
+    const float u = fminf(fmaxf(m.ax * (float)x + m.bx, 0.0f), (float)(sw - 1u));
+    const float v = fminf(fmaxf(m.ay * (float)y + m.by, 0.0f), (float)(sh - 1u));
+    if (!bilinear) {
+        const uint32_t iu = min((uint32_t)roundf(u), sw - 1u), iv = min((uint32_t)roundf(v), sh - 1u);
+        for (uint32_t k = 0; k < C; ++k) d[k] = __ldg(s + ((size_t)iv * sw + iu) * C + k);
+        return;
+    }
+    const uint32_t iu = (uint32_t)u, iv = (uint32_t)v;  // trunc, u,v >= 0
+    const float fu = u - truncf(u), fv = v - truncf(v);
+    const bool hx = iu + 1u < sw, hy = iv + 1u < sh;
+    const size_t b00 = ((size_t)iv * sw + iu) * C;
+    const size_t b01 = hx ? b00 + C : b00;
+    const size_t b10 = hy ? b00 + (size_t)sw * C : b00;
+    const size_t b11 = (hx && hy) ? b00 + (size_t)sw * C + C : b00;
+    const float fuu = 1.0f - fu, fvv = 1.0f - fv;
+    const float w00 = fvv * fuu, w10 = fvv * fu, w01 = fv * fuu, w11 = fv * fu;
+    for (uint32_t k = 0; k < C; ++k)
+        d[k] = w00 * __ldg(s + b00 + k) + w10 * __ldg(s + b01 + k) + w01 * __ldg(s + b10 + k) + w11 * __ldg(s + b11 + k);
+}
+
+// ── u8 Q14 bilinear ─────────────────────────────────────────────────────────────────────────
+// bilinear_tap (resize/bilinear.rs:25-38) in f64 on the device — one per axis per thread; the
+// result is identical to the host LUT because it is the same IEEE f64 expression.
+__device__ __forceinline__ void bilinear_tap_q14(uint32_t i, double scale, uint32_t src_len, uint32_t* ofs, uint32_t* fq) {
+    const double s = __dadd_rn(__dmul_rn((double)i + 0.5, scale), -0.5);
+    long long i0 = (long long)floor(s);
+    double f = s - (double)i0;
+    if (i0 < 0) { i0 = 0; f = 0.0; }
+    else if (i0 >= (long long)src_len - 1) { i0 = (long long)src_len - 2; f = 1.0; }
+    const double q = round(__dmul_rn(f, 16384.0));
+    *fq = min((uint32_t)q, 16384u);
+    *ofs = (uint32_t)i0;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                 uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh,
+                                                                 double scale_x, double scale_y) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sw * sh * C;
+    uint8_t* d = dst + ((size_t)blockIdx.z * dw * dh + (size_t)y * dw + x) * C;
+    uint32_t xi, fx, yi, fy;
+    bilinear_tap_q14(x, scale_x, sw, &xi, &fx);
+    bilinear_tap_q14(y, scale_y, sh, &yi, &fy);
+    const unsigned long long fx1 = 16384u - fx, fy1 = 16384u - fy;
+    const uint8_t* r0 = s + ((size_t)yi * sw + xi) * C;
+    const uint8_t* r1 = r0 + (size_t)sw * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        const unsigned long long p00 = r0[ch], p01 = r0[C + ch], p10 = r1[ch], p11 = r1[C + ch];
+        const unsigned long long top = p00 * fx1 + p01 * fx;
+        const unsigned long long bot = p10 * fx1 + p11 * fx;
+        d[ch] = (uint8_t)((top * fy1 + bot * (unsigned long long)fy + (1ull << 27)) >> 28);
+    }
+}
+
+static inline int check_batch(uint32_t batch) {
+    if (batch > 65535u) return fail(KB200_ERR_INVALID_ARGUMENT, "batch %u exceeds 65535 per call", batch);
+    return KB200_OK;
+}
+
+static int launch_resize_c3(int mode, kb200_stream_t stream, const float* src, size_t src_len, float* dst,
+                            size_t dst_len, uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, uint32_t batch,
+                            int mapping, const float* mean, const float* stdv) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_geometry(sw, sh, dw, dh, batch)); KB200_TRY(check_batch(batch));
+    if (mapping != KB200_MAP_HALF_PIXEL && mapping != KB200_MAP_ALIGN_CORNERS)
+        return fail(KB200_ERR_INVALID_ARGUMENT, "unknown pixel mapping %d", mapping);
+    KB200_TRY(check_slice("dst", dst_len, (size_t)dw * dh * 3 * batch));
+    KB200_TRY(check_slice("src", src_len, (size_t)sw * sh * 3 * batch));
+    float is[3] = {1, 1, 1}, mn[3] = {0, 0, 0};
+    if (mode == 2) {
+        if (!mean || !stdv) return fail(KB200_ERR_INVALID_ARGUMENT, "mean/std must not be null");
+        if (stdv[0] == 0.0f || stdv[1] == 0.0f || stdv[2] == 0.0f)
+            return fail(KB200_ERR_INVALID_ARGUMENT, "std must be non-zero for all channels");  // cuda/resize.rs:606-610
+        for (int c = 0; c < 3; ++c) { is[c] = 1.0f / stdv[c]; mn[c] = mean[c]; }
+    }
+    AxisMap m;
+    mapping_coeffs(mapping, sw, dw, &m.ax, &m.bx);
+    mapping_coeffs(mapping, sh, dh, &m.ay, &m.by);
+    dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
+    cudaStream_t s = as_stream(stream);
+    if (mode == 0) resize_f32_c3_kernel<0><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, m, 0, 0, 0, 1, 1, 1);
+    else if (mode == 1) resize_f32_c3_kernel<1><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, m, 0, 0, 0, 1, 1, 1);
+    else resize_f32_c3_kernel<2><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, m, mn[0], mn[1], mn[2], is[0], is[1], is[2]);
+    return check_launch("resize_f32_c3_kernel");
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+extern "C" {
+
+KB200_API int kb200_resize_bilinear_f32_c3(kb200_stream_t stream, const float* src, size_t src_len, float* dst,
+                                           size_t dst_len, uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh,
+                                           uint32_t batch, int mapping) {
+    return launch_resize_c3(1, stream, src, src_len, dst, dst_len, sw, sh, dw, dh, batch, mapping, nullptr, nullptr);
+}
+
+KB200_API int kb200_resize_nearest_f32_c3(kb200_stream_t stream, const float* src, size_t src_len, float* dst,
+                                          size_t dst_len, uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh,
+                                          uint32_t batch, int mapping) {
+    return launch_resize_c3(0, stream, src, src_len, dst, dst_len, sw, sh, dw, dh, batch, mapping, nullptr, nullptr);
+}
+
+KB200_API int kb200_resize_bilinear_normalize_f32_c3(kb200_stream_t stream, const float* src, size_t src_len,
+                                                     float* dst, size_t dst_len, uint32_t sw, uint32_t sh,
+                                                     uint32_t dw, uint32_t dh, uint32_t batch, const float mean[3],
+                                                     const float stdv[3], int mapping) {
+    return launch_resize_c3(2, stream, src, src_len, dst, dst_len, sw, sh, dw, dh, batch, mapping, mean, stdv);
+}
+
+KB200_API int kb200_resize_f32(kb200_stream_t stream, const float* src, size_t src_len, float* dst, size_t dst_len,
+                               uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, uint32_t C, uint32_t batch,
+                               int interp) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_geometry(sw, sh, dw, dh, batch)); KB200_TRY(check_batch(batch));
+    if (C == 0 || C > 4) return fail(KB200_ERR_UNSUPPORTED, "CUDA resize supports 1..4 channels only, got %u", C);
+    if (interp != KB200_INTERP_NEAREST && interp != KB200_INTERP_BILINEAR)
+        return fail(KB200_ERR_UNSUPPORTED, "CUDA resize supports Nearest/Bilinear only (mode %d)", interp);
+    KB200_TRY(check_slice("dst", dst_len, (size_t)dw * dh * C * batch));
+    KB200_TRY(check_slice("src", src_len, (size_t)sw * sh * C * batch));
+    cudaStream_t s = as_stream(stream);
+    if (sw == dw && sh == dh) {  // resize/mod.rs:134-137: same size is a copy
+        cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)sw * sh * C * batch * sizeof(float), cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e));
+        return KB200_OK;
+    }
+    AxisMap m;
+    mapping_coeffs(KB200_MAP_HALF_PIXEL, sw, dw, &m.ax, &m.bx);
+    mapping_coeffs(KB200_MAP_HALF_PIXEL, sh, dh, &m.ay, &m.by);
+    dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
+    resize_f32_generic_kernel<<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, C, m, interp == KB200_INTERP_BILINEAR);
+    return check_launch("resize_f32_generic_kernel");
+}
+
+KB200_API int kb200_resize_bilinear_u8(kb200_stream_t stream, const uint8_t* src, size_t src_len, uint8_t* dst,
+                                       size_t dst_len, uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh,
+                                       uint32_t C, uint32_t batch) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_geometry(sw, sh, dw, dh, batch)); KB200_TRY(check_batch(batch));
+    if (!(C == 1 || C == 3 || C == 4)) return fail(KB200_ERR_UNSUPPORTED, "u8 bilinear resize supports 1, 3 or 4 channels, got %u", C);
+    if (sw < 2 || sh < 2) return fail(KB200_ERR_INVALID_ARGUMENT, "u8 bilinear resize needs a source of at least 2x2, got %ux%u", sw, sh);  // resize/mod.rs:318-320
+    KB200_TRY(check_slice("dst", dst_len, (size_t)dw * dh * C * batch));
+    KB200_TRY(check_slice("src", src_len, (size_t)sw * sh * C * batch));
+    const double scale_x = (double)sw / (double)dw, scale_y = (double)sh / (double)dh;
+    dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
+    cudaStream_t s = as_stream(stream);
+    if (C == 1) resize_bilinear_u8_kernel<1><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
+    else if (C == 3) resize_bilinear_u8_kernel<3><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
+    else resize_bilinear_u8_kernel<4><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
+    return check_launch("resize_bilinear_u8_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+"""The `kornia-imgproc` operator surface of the hot path, over the C-ABI (include/kornia_b200.h).
+
+Same names, argument meaning and error behaviour as the reference's public functions (cited per
+function; paths relative to crates/kornia-imgproc/src).  Every op takes `Image`s (HWC, or NHWC for a
+batch), checks residency like `pair_residency` (cuda/dispatch.rs:105) and enqueues ONE kernel on the
+current CUDA stream of the images' device — asynchronous, no sync, no allocation of outputs.
+
+The reference's host (rayon/SIMD) path is not part of this build and there is no CPU fallback:
+host operands raise `ImageError(UnsupportedDevice)`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import torch
+
+from . import _lib
+from .image import Image, ImageError, ImageSize, InterpolationMode, pair_residency
+
+# kb200_cpu_leaf: which CPU leaf of the reference the f32 bits must equal where its scalar and SIMD
+# leaves differ (FMA vs mul+add).  The reference's x86_64 hosts with AVX2+FMA run the FMA leaves.
+LEAF_SCALAR, LEAF_X86_AVX2_FMA, LEAF_AARCH64_NEON = 0, 1, 2
+DEFAULT_LEAF = LEAF_X86_AVX2_FMA
+
+_INTERP = {InterpolationMode.Nearest: 0, InterpolationMode.Bilinear: 1}
+
+
+def _stream(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _check(status: int) -> None:
+    if status != _lib.OK:
+        raise ImageError.Cuda(_lib.last_error())
+
+
+def _prep(op: str, *images: Image) -> torch.device:
+    dev = pair_residency(op, *images)
+    _lib.set_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    return dev
+
+
+def _interp_code(op: str, mode: InterpolationMode) -> int:
+    if mode not in _INTERP:
+        # Bicubic / Lanczos exist in the reference but are outside this tier's hot path
+        raise ImageError.UnsupportedInterpolation(mode)
+    return _INTERP[mode]
+
+
+def _same_batch(src: Image, dst: Image) -> int:
+    if src.batch != dst.batch:
+        raise ImageError.InvalidImageSize(src.batch, 0, dst.batch, 0)
+    return src.batch
+
+
+def _expect_dtype(im: Image, dtype, what: str) -> None:
+    if im.dtype != dtype:
+        raise ImageError.DtypeMismatch(dtype, im.dtype)
+
+
+# ── resize ───────────────────────────────────────────────────────────────────
+def resize(src: Image, dst: Image, interpolation: InterpolationMode) -> None:
+    """resize/mod.rs:114 `resize<C>(src, dst, mode)` — f32, half-pixel grid, bit-identical to the CPU path."""
+    code = _interp_code("resize", interpolation)
+    dev = _prep("resize", src, dst)
+    _expect_dtype(src, torch.float32, "src"); _expect_dtype(dst, torch.float32, "dst")
+    c = src.num_channels()
+    if dst.num_channels() != c:
+        raise ImageError.InvalidChannelShape(dst.num_channels(), c)
+    n = _same_batch(src, dst)
+    l = _lib.lib()
+    args = (_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
+            src.cols(), src.rows(), dst.cols(), dst.rows())
+    if c == 3 and not (src.size() == dst.size()):
+        fn = l.kb200_resize_bilinear_f32_c3 if code == 1 else l.kb200_resize_nearest_f32_c3
+        _check(fn(*args, n, 0))
+    else:
+        _check(l.kb200_resize_f32(*args, c, n, code))
+
+
+def resize_bilinear_normalize(src: Image, dst: Image, mean: Sequence[float], std: Sequence[float],
+                              align_corners: bool = False) -> None:
+    """cuda/resize.rs:580 `launch_resize_bilinear_normalize_cuda` — bilinear + (v-mean)/std, HWC out."""
+    dev = _prep("resize_bilinear_normalize", src, dst)
+    _expect_dtype(src, torch.float32, "src"); _expect_dtype(dst, torch.float32, "dst")
+    if src.num_channels() != 3 or dst.num_channels() != 3:
+        raise ImageError.Cuda("CUDA resize supports 3-channel f32 images only; move the images to the host (Image::to_host) to use the CPU path")
+    n = _same_batch(src, dst)
+    _check(_lib.lib().kb200_resize_bilinear_normalize_f32_c3(
+        _stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), src.cols(), src.rows(),
+        dst.cols(), dst.rows(), n, _lib.f3(mean), _lib.f3(std), 1 if align_corners else 0))
+
+
+def resize_fast_u8(src: Image, dst: Image, interpolation: InterpolationMode = InterpolationMode.Bilinear) -> None:
+    """resize/mod.rs:348 `resize_fast_u8_aa` — the generic Q14 bilinear arm (resize/bilinear.rs:70).
+    The exact-2x pyramid arms and nearest/bicubic/lanczos are "next" rows."""
+    if interpolation != InterpolationMode.Bilinear:
+        raise ImageError.UnsupportedInterpolation(interpolation)
+    dev = _prep("resize_fast_u8", src, dst)
+    _expect_dtype(src, torch.uint8, "src"); _expect_dtype(dst, torch.uint8, "dst")
+    c = src.num_channels()
+    if c not in (1, 3, 4):
+        raise ImageError.UnsupportedChannelCount(c)
+    if src.cols() < 2 or src.rows() < 2:
+        raise ImageError.InvalidImageSize(src.cols(), src.rows(), 2, 2)
+    n = _same_batch(src, dst)
+    _check(_lib.lib().kb200_resize_bilinear_u8(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(),
+                                               dst.numel(), src.cols(), src.rows(), dst.cols(), dst.rows(), c, n))
+
+
+class NormalizeParams:
+    """resize/fused.rs:17-38 — scale = 1/(std*255), bias = -mean/std (f32 arithmetic)."""
+
+    def __init__(self, scale, bias):
+        self.scale = [float(v) for v in scale]
+        self.bias = [float(v) for v in bias]
+
+    @staticmethod
+    def from_mean_std(mean, std) -> "NormalizeParams":
+        m = torch.tensor(list(mean), dtype=torch.float32)
+        s = torch.tensor(list(std), dtype=torch.float32)
+        scale = torch.tensor(1.0, dtype=torch.float32) / (s * torch.tensor(255.0, dtype=torch.float32))
+        bias = -m / s
+        return NormalizeParams(scale.tolist(), bias.tolist())
+
+
+def resize_normalize_to_tensor_u8_to_f32_bilinear(src, dst_w: int, dst_h: int, scale, bias, out: torch.Tensor | None = None,
+                                                  leaf: int = DEFAULT_LEAF) -> torch.Tensor:
+    """resize/fused.rs:147 — u8 HWC (or NHWC) → f32 CHW ([N,3,dst_h,dst_w]) bilinear (half-pixel, non-AA)
+    resize + `sample*scale[c] + bias[c]`; exact 2x dispatches to the box average (fused.rs:181-183)."""
+    t = src.data if isinstance(src, Image) else src
+    if not t.is_cuda:
+        raise ImageError.HostPathNotBuilt("resize_normalize_to_tensor_u8_to_f32_bilinear")
+    if t.dtype != torch.uint8:
+        raise ImageError.DtypeMismatch(torch.uint8, t.dtype)
+    if not t.is_contiguous():
+        raise ImageError.ImageDataNotContiguous()
+    if t.dim() == 3:
+        t = t.unsqueeze(0)
+    n, sh, sw, c = t.shape
+    if c != 3:
+        raise ImageError.InvalidChannelShape(t.numel(), n * sh * sw * 3)
+    if out is None:
+        out = torch.empty((n, 3, dst_h, dst_w), dtype=torch.float32, device=t.device)
+    else:
+        if out.device != t.device:
+            raise ImageError.DeviceMismatch() if out.is_cuda else ImageError.MixedResidency()
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != n * 3 * dst_h * dst_w:
+            raise ImageError.InvalidChannelShape(out.numel(), n * 3 * dst_h * dst_w)
+    dev = t.device
+    _lib.set_device(dev.index)
+    _check(_lib.lib().kb200_resize_normalize_chw_u8_f32(_stream(dev), t.data_ptr(), t.numel(), out.data_ptr(), out.numel(),
+                                                       sw, sh, dst_w, dst_h, n, _lib.f3(scale), _lib.f3(bias), leaf))
+    return out
+
+
+# ── warps ────────────────────────────────────────────────────────────────────
+def invert_affine_transform(m: Sequence[float]) -> list[float]:
+    """warp/affine.rs:18."""
+    out = (C.c_float * 6)()
+    _lib.lib().kb200_invert_affine_transform(_lib.f3(m, 6), out)
+    return list(out)
+
+
+def get_rotation_matrix2d(center: tuple[float, float], angle: float, scale: float) -> list[float]:
+    """warp/affine.rs:70 — f32 arithmetic with libm cosf/sinf (the reference's f32::cos/sin)."""
+    out = (C.c_float * 6)()
+    _lib.lib().kb200_get_rotation_matrix2d(center[0], center[1], angle, scale, out)
+    return list(out)
+
+
+def invert_homography(h: Sequence[float]):
+    """warp/perspective.rs:41 — None for a singular matrix."""
+    out = (C.c_float * 9)()
+    st = _lib.lib().kb200_invert_homography(_lib.f3(h, 9), out)
+    return None if st != _lib.OK else list(out)
+
+
+def _warp(op: str, fn_name: str, src: Image, dst: Image, m: Sequence[float], nm: int, interpolation: InterpolationMode) -> None:
+    code = _interp_code(op, interpolation)
+    dev = _prep(op, src, dst)
+    _expect_dtype(src, torch.float32, "src"); _expect_dtype(dst, torch.float32, "dst")
+    if src.num_channels() != 3 or dst.num_channels() != 3:  # warp/cuda.rs:36-38: no_gpu_kernel_err
+        raise ImageError.Cuda(f"CUDA {op} supports 3-channel f32 images only; move the images to the host (Image::to_host) to use the CPU path")
+    if len(m) != nm:
+        raise ValueError(f"{op}: expected {nm} matrix entries, got {len(m)}")
+    n = _same_batch(src, dst)
+    fn = getattr(_lib.lib(), fn_name)
+    _check(fn(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), src.cols(), src.rows(),
+              dst.cols(), dst.rows(), n, _lib.f3(m, nm), code))
+
+
+def warp_affine(src: Image, dst: Image, m: Sequence[float], interpolation: InterpolationMode) -> None:
+    """warp/affine.rs:123 — forward 2x3 `m` (inverted internally); pixels mapping outside the source are 0."""
+    _warp("warp_affine", "kb200_warp_affine_f32_c3", src, dst, m, 6, interpolation)
+
+
+def warp_perspective(src: Image, dst: Image, m: Sequence[float], interpolation: InterpolationMode) -> None:
+    """warp/perspective.rs:115 — forward 3x3 `m`; a singular matrix is an error; out-of-source pixels are
+    written 0 (the device twin's rule, cuda/warp_perspective.rs:81-84)."""
+    _warp("warp_perspective", "kb200_warp_perspective_f32_c3", src, dst, m, 9, interpolation)
+
+
+# ── filters ──────────────────────────────────────────────────────────────────
+def _filter_prep(op: str, src: Image, dst: Image):
+    dev = _prep(op, src, dst)
+    _expect_dtype(src, torch.float32, "src"); _expect_dtype(dst, torch.float32, "dst")
+    if src.size() != dst.size() or src.num_channels() != dst.num_channels():
+        raise ImageError.InvalidImageSize(src.cols(), src.rows(), dst.cols(), dst.rows())
+    return dev, _same_batch(src, dst)
+
+
+def separable_filter(src: Image, dst: Image, kernel_x: Sequence[float], kernel_y: Sequence[float]) -> None:
+    """filter/separable_filter.rs:166 — correlation, zero border, H then V; one fused kernel here."""
+    if len(kernel_x) == 0 or len(kernel_y) == 0:
+        raise ImageError.InvalidKernelLength(len(kernel_x), len(kernel_y))
+    dev, n = _filter_prep("separable_filter", src, dst)
+    _check(_lib.lib().kb200_separable_filter_f32(
+        _stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), None,
+        _lib.f3(kernel_x, len(kernel_x)), len(kernel_x), _lib.f3(kernel_y, len(kernel_y)), len(kernel_y),
+        src.cols(), src.rows(), src.num_channels(), n))
+
+
+def gaussian_blur(src: Image, dst: Image, kernel_size: tuple[int, int], sigma: tuple[float, float]) -> None:
+    """filter/ops.rs:116 — (0,0) kernel sizes / zero sigmas are auto-resolved exactly like the reference."""
+    dev, n = _filter_prep("gaussian_blur", src, dst)
+    l = _lib.lib()
+    kx, ky, sx, sy = C.c_uint32(), C.c_uint32(), C.c_float(), C.c_float()
+    if l.kb200_gaussian_resolve(kernel_size[0], kernel_size[1], sigma[0], sigma[1], C.byref(kx), C.byref(ky),
+                                C.byref(sx), C.byref(sy)) != _lib.OK:
+        sy_in = sigma[1] if sigma[1] > 0 else sigma[0]
+        raise ImageError.InvalidSigmaValue(sigma[0], sy_in)
+    _check(l.kb200_gaussian_blur_f32(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
+                                     src.cols(), src.rows(), src.num_channels(), n, kernel_size[0], kernel_size[1],
+                                     sigma[0], sigma[1]))
+
+
+def gaussian_kernel_1d(kernel_size: int, sigma: float) -> list[float]:
+    """filter/kernels.rs:25."""
+    out = (C.c_float * kernel_size)()
+    _lib.lib().kb200_gaussian_kernel_1d(kernel_size, sigma, out)
+    return list(out)
+
+
+def sobel_kernel_1d(kernel_size: int):
+    """filter/kernels.rs:55."""
+    if kernel_size == 3:
+        return [-1.0, 0.0, 1.0], [1.0, 2.0, 1.0]
+    if kernel_size == 5:
+        return [-1.0, -2.0, 0.0, 2.0, 1.0], [1.0, 4.0, 6.0, 4.0, 1.0]
+    raise ImageError.InvalidKernelLength(kernel_size, kernel_size)
+
+
+def sobel(src: Image, dst: Image, kernel_size: int) -> None:
+    """filter/ops.rs:174 — sqrt(gx² + gy²) of the two separable gradients, fused in one kernel."""
+    sobel_kernel_1d(kernel_size)
+    dev, n = _filter_prep("sobel", src, dst)
+    _check(_lib.lib().kb200_sobel_f32(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
+                                      src.cols(), src.rows(), src.num_channels(), n, kernel_size))
+
+
+# ── colour ───────────────────────────────────────────────────────────────────
+def gray_from_rgb(src: Image, dst: Image, leaf: int = LEAF_SCALAR) -> None:
+    """color/gray/mod.rs:104 `gray_from_rgb` (f32; `Rgbf32::convert`, color/convert.rs:42).
+    leaf=LEAF_SCALAR reproduces the reference's CUDA kernel and scalar CPU leaf
+    (`0.299r + 0.587g + 0.114b`, unfused); LEAF_X86_AVX2_FMA its AVX2 leaf."""
+    dev = _prep("gray_from_rgb", src, dst)
+    if src.num_channels() != 3 or dst.num_channels() != 1:
+        raise ImageError.InvalidChannelShape(dst.num_channels(), 1)
+    if src.size() != dst.size() or src.batch != dst.batch:
+        raise ImageError.InvalidImageSize(src.cols(), src.rows(), dst.cols(), dst.rows())
+    npx = src.rows() * src.cols() * src.batch
+    l = _lib.lib()
+    if src.dtype == torch.float32 and dst.dtype == torch.float32:
+        _check(l.kb200_gray_from_rgb_f32(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), npx, leaf))
+    elif src.dtype == torch.uint8 and dst.dtype == torch.uint8:
+        _check(l.kb200_gray_from_rgb_u8(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), npx))
+    else:
+        raise ImageError.DtypeMismatch(src.dtype, dst.dtype)
+
+
+def _raw_frames(src, what: str) -> torch.Tensor:
+    t = src.data if isinstance(src, Image) else src
+    if not t.is_cuda:
+        raise ImageError.HostPathNotBuilt(what)
+    if t.dtype != torch.uint8:
+        raise ImageError.DtypeMismatch(torch.uint8, t.dtype)
+    if not t.is_contiguous():
+        raise ImageError.ImageDataNotContiguous()
+    return t
+
+
+def rgb_from_nv12(src, dst: Image) -> None:
+    """color/yuv/mod.rs:235 — `src`: u8 tensor holding, per frame, w*h Y bytes then w*h/2 interleaved UV
+    bytes ([len] or [N,len]); BT.601 limited, Q20, bit-exact."""
+    t = _raw_frames(src, "rgb_from_nv12")
+    if not dst.is_device:
+        raise ImageError.MixedResidency()
+    if t.device != dst.device:
+        raise ImageError.DeviceMismatch()
+    _expect_dtype(dst, torch.uint8, "dst")
+    w, h, n = dst.cols(), dst.rows(), dst.batch
+    need = w * h * 3 // 2 * n
+    if dst.num_channels() != 3 or t.numel() != need:
+        raise ImageError.InvalidImageSize(t.numel(), 1, need, 1)  # check_dst_size, color/yuv/mod.rs:186-207
+    _lib.set_device(t.device.index)
+    _check(_lib.lib().kb200_rgb_from_nv12_u8(_stream(t.device), t.data_ptr(), t.numel(), dst.data.data_ptr(), dst.numel(), w, h, n))
+
+
+def rgb_from_yuyv(src, dst: Image) -> None:
+    """color/yuv/mod.rs:209 (impl_packed422!, Yuyv)."""
+    t = _raw_frames(src, "rgb_from_yuyv")
+    if not dst.is_device:
+        raise ImageError.MixedResidency()
+    if t.device != dst.device:
+        raise ImageError.DeviceMismatch()
+    _expect_dtype(dst, torch.uint8, "dst")
+    w, h, n = dst.cols(), dst.rows(), dst.batch
+    need = w * h * 2 * n
+    if dst.num_channels() != 3 or t.numel() != need:
+        raise ImageError.InvalidImageSize(t.numel(), 1, need, 1)
+    _lib.set_device(t.device.index)
+    _check(_lib.lib().kb200_rgb_from_yuyv_u8(_stream(t.device), t.data_ptr(), t.numel(), dst.data.data_ptr(), dst.numel(), w, h, n))
+
+
+# ── normalize / statistics ───────────────────────────────────────────────────
+def normalize_mean_std(src: Image, dst: Image, mean: Sequence[float], std: Sequence[float]) -> None:
+    """normalize.rs:56 — (x - mean[c]) / std[c], true division."""
+    dev = _prep("normalize_mean_std", src, dst)
+    _expect_dtype(src, torch.float32, "src"); _expect_dtype(dst, torch.float32, "dst")
+    if src.size() != dst.size() or src.batch != dst.batch or src.num_channels() != dst.num_channels():
+        raise ImageError.InvalidImageSize(src.cols(), src.rows(), dst.cols(), dst.rows())
+    c = src.num_channels()
+    if len(mean) != c or len(std) != c:
+        raise ValueError("mean/std must have one entry per channel")
+    _check(_lib.lib().kb200_normalize_mean_std_f32(_stream(dev), src.data.data_ptr(), dst.data.data_ptr(),
+                                                  src.rows() * src.cols() * src.batch, c, _lib.f3(mean, c), _lib.f3(std, c)))
+
+
+def find_min_max(image: Image) -> tuple[float, float]:
+    """normalize.rs:123 — synchronises (returns host scalars)."""
+    if not image.is_device:
+        raise ImageError.HostPathNotBuilt("find_min_max")
+    if image.numel() == 0:
+        raise ImageError.ImageDataNotInitialized()
+    _expect_dtype(image, torch.float32, "image")
+    dev = image.device
+    _lib.set_device(dev.index)
+    mm = torch.empty(2, dtype=torch.float32, device=dev)
+    _check(_lib.lib().kb200_find_min_max_f32(_stream(dev), image.data.data_ptr(), image.numel(), mm.data_ptr()))
+    lo, hi = mm.tolist()
+    return lo, hi
+
+
+def normalize_min_max(src: Image, dst: Image, min: float, max: float) -> None:
+    """normalize.rs:191 — (x - min_v) * (max - min) / (max_v - min_v) + min; min_v/max_v found on the device, no sync."""
+    dev = _prep("normalize_min_max", src, dst)
+    _expect_dtype(src, torch.float32, "src"); _expect_dtype(dst, torch.float32, "dst")
+    if src.size() != dst.size() or src.batch != dst.batch or src.num_channels() != dst.num_channels():
+        raise ImageError.InvalidImageSize(src.cols(), src.rows(), dst.cols(), dst.rows())
+    if src.numel() == 0:
+        raise ImageError.ImageDataNotInitialized()
+    mm = torch.empty(2, dtype=torch.float32, device=dev)
+    l = _lib.lib()
+    _check(l.kb200_find_min_max_f32(_stream(dev), src.data.data_ptr(), src.numel(), mm.data_ptr()))
+    _check(l.kb200_normalize_min_max_f32(_stream(dev), src.data.data_ptr(), dst.data.data_ptr(), src.numel(), min, max, mm.data_ptr()))
+
+
+def normalize_rgb_u8(src, dst, npixels: int, scale: Sequence[float], offset: Sequence[float], leaf: int = DEFAULT_LEAF) -> None:
+    """normalize.rs:235 — u8 RGB → f32: src[i]*scale[ch] + offset[ch] (`src`, `dst`: tensors or Images)."""
+    s = src.data if isinstance(src, Image) else src
+    d = dst.data if isinstance(dst, Image) else dst
+    if not (s.is_cuda and d.is_cuda):
+        raise ImageError.HostPathNotBuilt("normalize_rgb_u8") if not (s.is_cuda or d.is_cuda) else ImageError.MixedResidency()
+    if s.device != d.device:
+        raise ImageError.DeviceMismatch()
+    if s.dtype != torch.uint8 or d.dtype != torch.float32:
+        raise ImageError.DtypeMismatch("u8->f32", (s.dtype, d.dtype))
+    if s.numel() < npixels * 3 or d.numel() < npixels * 3:
+        raise ImageError.InvalidChannelShape(min(s.numel(), d.numel()), npixels * 3)
+    _lib.set_device(s.device.index)
+    _check(_lib.lib().kb200_normalize_rgb_u8_f32(_stream(s.device), s.data_ptr(), d.data_ptr(), npixels, _lib.f3(scale), _lib.f3(offset), leaf))
+
+
+def std_mean_sums(image: Image) -> torch.Tensor:
+    """The six exact integer sums (Σp per channel, Σp² per channel) as a device uint64[6] tensor — no sync.
+    Shard-wise sums add (one all-reduce over 6 integers gives the global statistic)."""
+    if not image.is_device:
+        raise ImageError.HostPathNotBuilt("std_mean")
+    _expect_dtype(image, torch.uint8, "image")
+    if image.num_channels() != 3:
+        raise ImageError.InvalidChannelShape(image.num_channels(), 3)
+    dev = image.device
+    _lib.set_device(dev.index)
+    sums = torch.empty(6, dtype=torch.int64, device=dev)
+    _check(_lib.lib().kb200_std_mean_u8_c3(_stream(dev), image.data.data_ptr(), image.rows() * image.cols() * image.batch, sums.data_ptr()))
+    return sums
+
+
+def std_mean_finalize(sums, npixels: int) -> tuple[list[float], list[float]]:
+    """core.rs:58-66 in f64, same operation order.  Returns (std, mean) like the reference."""
+    arr = (C.c_uint64 * 6)(*[int(v) for v in sums])
+    std, mean = (C.c_double * 3)(), (C.c_double * 3)()
+    _lib.lib().kb200_std_mean_finalize(arr, npixels, std, mean)
+    return list(std), list(mean)
+
+
+def std_mean(image: Image) -> tuple[list[float], list[float]]:
+    """core.rs:42 `std_mean(&Image<u8,3>) -> (std, mean)` (synchronises to return host f64s)."""
+    sums = std_mean_sums(image).tolist()
+    return std_mean_finalize(sums, image.rows() * image.cols() * image.batch)

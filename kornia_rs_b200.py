@@ -1,0 +1,13 @@
+"""Import shim: the package directory is `kornia-rs_b200/` (a hyphen is not importable), so this
+module loads it under the importable name `kornia_rs_b200`."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "kornia-rs_b200")
+_spec = importlib.util.spec_from_file_location(
+    "kornia_rs_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir]
+)
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["kornia_rs_b200"] = _mod
+_spec.loader.exec_module(_mod)
