@@ -7,6 +7,8 @@
 // `fma_bulk` = number of leading destination columns whose arithmetic is the reference's FMA leaf;
 // columns ≥ fma_bulk use the scalar (mul, add) leaf — so the output is bit-identical to what the
 // reference produces on the chosen CPU (x86 AVX2+FMA: bulk = dst_w & ~7, or & ~15 on the 2x path).
+#include <algorithm>
+
 #include "kb200_common.cuh"
 
 namespace kb200 {
@@ -114,10 +116,282 @@ KB200_API int kb200_resize_normalize_chw_u8_f32(kb200_stream_t stream, const uin
 
 }  // extern "C"
 
+// ─────────────────────────────────────────────────────────────────────────────────────────────
+// Row-span staged kernel (the config-2 fast path).
+//
+// ncu history (profiles/r1_cfg2_*.md): the gather kernel above executes 170 warp-instructions per
+// output pixel at 79 % issue-slot utilisation with DRAM at 60 % — instruction-bound, not memory-bound.
+// This kernel moves the source reads off the LSU, cuts the instruction count and keeps a deep queue of
+// TMA copies in flight:
+//
+//   * work unit = (image, column tile of TW destination columns, chunk of RC destination rows); CTAs are
+//     persistent and walk their units with carry arithmetic (no integer division in the loop).
+//   * per destination row, the two source rows it taps are copied — only the byte span
+//     [x0(first col), x1(last col)] the column tile touches, rounded out to 16 B — global -> shared by
+//     the TMA engine (cp.async.bulk 1-D, SASS UBLKCP), completion counted on an mbarrier (expect_tx).
+//     Source rows no destination row taps (1 of every 3 at scale 3) are never addressed.
+//   * STAGES-deep ring, one destination row per stage, running continuously across units.  Warp 8 is the
+//     producer (one elected lane: wait `empty`, publish the row's y-weight, issue the 2 copies); warps
+//     0-7 are consumers (wait `full`, compute one row, arrive on `empty`).  No __syncthreads in the loop.
+//   * a consumer thread owns ONE destination column for the whole unit: the x-side of the sampler
+//     (fx, x0, wx, smem byte offset, funnel shift) is computed once per unit and lives in registers.
+//   * taps are read as three aligned 32-bit words per source row and funnel-shifted into place; a byte
+//     becomes a float with one PRMT into the mantissa of 2^23; `b - a` is formed on the biased values
+//     (exact) and only the base taps are unbiased (one FADD).
+//   * stores: a warp writes 32 consecutive floats of one channel plane = one full 128-B line.
+//
+// Arithmetic is identical to the gather kernel (and therefore to the reference leaf selected).
 namespace kb200 {
-// Placeholder until the row-span staged kernel lands (round-1 step 2): never handles.
-int launch_fused_resize_staged(cudaStream_t, const uint8_t*, float*, const FusedParams&, uint32_t, bool* handled) {
+
+static constexpr int FS_TW = 256;              // destination columns per unit = consumer threads per CTA
+static constexpr int FS_STAGES = 8;            // ring depth (destination rows in flight per CTA)
+static constexpr int FS_THREADS = FS_TW + 32;  // + producer warp
+
+struct FusedStagedParams {
+    FusedParams p;
+    uint32_t tiles_x, chunks_y, rows_per_chunk, nunits;
+    uint32_t slot_bytes;   // bytes reserved per staged source-row span (multiple of 128)
+    uint32_t row_bytes;    // sw * 3
+    // CTA stride decomposed for the carry walk: gridDim.x = (dimg*chunks_y + dcy)*tiles_x + dtx
+    uint32_t dtx, dcy, dimg;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared::cta through the TMA engine; bytes % 16 == 0, both addresses 16-B aligned.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// half-pixel source coordinate of the fused path — resize/fused.rs:196-201 (unfused mul/add)
+__device__ __forceinline__ void fused_axis(uint32_t d, float scale, uint32_t src_len, uint32_t* i0, uint32_t* i1, float* w) {
+    const float f = fmaxf(((float)d + 0.5f) * scale - 0.5f, 0.0f);
+    const uint32_t a = min((uint32_t)f, src_len - 1u);
+    *i0 = a;
+    *i1 = min(a + 1u, src_len - 1u);
+    *w = f - (float)a;
+}
+
+// (tx, chunk, img) walk: advance by one CTA stride without dividing.
+struct UnitWalk {
+    uint32_t tx, cy, img;
+    __device__ __forceinline__ void init(uint32_t u, const FusedStagedParams& P) {
+        const uint32_t per_img = P.tiles_x * P.chunks_y;
+        img = u / per_img;
+        const uint32_t t = u - img * per_img;
+        cy = t / P.tiles_x;
+        tx = t - cy * P.tiles_x;
+    }
+    __device__ __forceinline__ void advance(const FusedStagedParams& P) {
+        tx += P.dtx; cy += P.dcy; img += P.dimg;
+        if (tx >= P.tiles_x) { tx -= P.tiles_x; ++cy; }
+        if (cy >= P.chunks_y) { cy -= P.chunks_y; ++img; }
+        if (cy >= P.chunks_y) { cy -= P.chunks_y; ++img; }
+    }
+};
+
+// One destination row for one destination column out of a staged pair of source-row spans.
+template <bool FUSED_LEAF, bool EDGE>
+__device__ __forceinline__ void fs_row(const uint8_t* __restrict__ rp, uint32_t slot_bytes, uint32_t shft, float wx, float wy,
+                                       float s0, float s1, float s2, float o0, float o1, float o2, float& q0, float& q1, float& q2) {
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(rp);
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(rp + slot_bytes);
+    const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
+    const uint32_t c0 = r1[0], c1 = r1[1], c2 = r1[2];
+    uint32_t lo0 = __funnelshift_r(a0, a1, shft), hi0 = __funnelshift_r(a1, a2, shft);  // bytes off..off+3 | off+4..off+7
+    uint32_t lo1 = __funnelshift_r(c0, c1, shft), hi1 = __funnelshift_r(c1, c2, shft);
+    if (EDGE) {  // right image edge: the +1 tap replicates x0 — bytes 3..5 := bytes 0..2
+        hi0 = __byte_perm(lo0, 0, 0x4421); lo0 = __byte_perm(lo0, 0, 0x0210);
+        hi1 = __byte_perm(lo1, 0, 0x4421); lo1 = __byte_perm(lo1, 0, 0x0210);
+    }
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // biased floats 2^23 + byte: a = tap(x0,y0), b = tap(x1,y0), c = tap(x0,y1), d = tap(x1,y1)
+        const float ab = __uint_as_float(__byte_perm(lo0, 0x4B000000u, 0x7650u + (uint32_t)c));
+        const float cb = __uint_as_float(__byte_perm(lo1, 0x4B000000u, 0x7650u + (uint32_t)c));
+        const float bb = __uint_as_float(c == 0 ? __byte_perm(lo0, 0x4B000000u, 0x7653u) : __byte_perm(hi0, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
+        const float db = __uint_as_float(c == 0 ? __byte_perm(lo1, 0x4B000000u, 0x7653u) : __byte_perm(hi1, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
+        const float a = ab - 8388608.0f, cc = cb - 8388608.0f;  // exact
+        const float dba = bb - ab, ddc = db - cb;                 // exact: (2^23+b) - (2^23+a) = b - a
+        const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), bi = c == 0 ? o0 : (c == 1 ? o1 : o2);
+        if (FUSED_LEAF) {  // resize/fused.rs:475-478
+            const float top = fmaf(dba, wx, a);
+            const float bot = fmaf(ddc, wx, cc);
+            res[c] = fmaf(fmaf(bot - top, wy, top), sc, bi);
+        } else {           // resize/fused.rs:286-317
+            const float top = a + wx * dba;
+            const float bot = cc + wx * ddc;
+            const float val = top + wy * (bot - top);
+            res[c] = val * sc + bi;
+        }
+    }
+    q0 = res[0]; q1 = res[1]; q2 = res[2];
+}
+
+__global__ void __launch_bounds__(FS_THREADS) fused_resize_staged_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                                         const __grid_constant__ FusedStagedParams P) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[FS_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[FS_STAGES];
+    __shared__ float wy_s[FS_STAGES];
+    const FusedParams& p = P.p;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t stage_bytes = P.slot_bytes * 2u;
+    const size_t frame_bytes = (size_t)P.row_bytes * p.sh;
+    const size_t plane = (size_t)p.dw * p.dh;
+
+    if (tid == 0) {
+        for (int s = 0; s < FS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], FS_TW / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    UnitWalk w;
+    w.init(blockIdx.x, P);
+    uint32_t k = 0;  // running row counter of this CTA: stage = k % STAGES, use = k / STAGES
+
+    if (tid >= FS_TW) {
+        // ── producer warp: one elected lane ──
+        if (tid != FS_TW) return;
+        for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x, w.advance(P)) {
+            const uint32_t dx0 = w.tx * FS_TW, dx1 = min(dx0 + FS_TW, p.dw) - 1u;
+            uint32_t xa, xb, tmp;
+            float wtmp;
+            fused_axis(dx0, p.scale_x, p.sw, &xa, &tmp, &wtmp);
+            fused_axis(dx1, p.scale_x, p.sw, &tmp, &xb, &wtmp);
+            const uint32_t b0 = (xa * 3u) & ~15u;                                 // span start, 16-B aligned
+            const uint32_t b1 = min(((xb * 3u + 3u) + 15u) & ~15u, P.row_bytes);  // span end (row_bytes % 16 == 0)
+            const uint32_t bytes = b1 - b0;
+            const uint8_t* frame = src + (size_t)w.img * frame_bytes + b0;
+            const uint32_t y_first = w.cy * P.rows_per_chunk, y_end = min(y_first + P.rows_per_chunk, p.dh);
+            for (uint32_t dy = y_first; dy < y_end; ++dy, ++k) {
+                const uint32_t stage = k % FS_STAGES, use = k / FS_STAGES;
+                if (use > 0) mbar_wait(&empty_bar[stage], (use - 1u) & 1u);  // consumers drained the previous tenant
+                uint32_t y0, y1;
+                float wy;
+                fused_axis(dy, p.scale_y, p.sh, &y0, &y1, &wy);
+                wy_s[stage] = wy;  // before the arrive(release): covered by the consumers' acquire on `full`
+                uint8_t* sbase = smem_raw + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], bytes * 2u);
+                tma_load_1d(sbase, frame + (size_t)y0 * P.row_bytes, bytes, &full_bar[stage]);
+                tma_load_1d(sbase + P.slot_bytes, frame + (size_t)y1 * P.row_bytes, bytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+
+    // ── consumer warps ──
+    const float s0 = p.scale[0], s1 = p.scale[1], s2 = p.scale[2];
+    const float o0 = p.bias[0], o1 = p.bias[1], o2 = p.bias[2];
+    const bool lane0 = (tid & 31u) == 0;
+    for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x, w.advance(P)) {
+        const uint32_t dx0 = w.tx * FS_TW;
+        const uint32_t x = dx0 + tid;
+        // x-side of the sampler, once per unit
+        uint32_t x0, x1, xa, tmp;
+        float wx, wtmp;
+        fused_axis(min(x, p.dw - 1u), p.scale_x, p.sw, &x0, &x1, &wx);
+        fused_axis(dx0, p.scale_x, p.sw, &xa, &tmp, &wtmp);
+        const uint32_t off = x0 * 3u - ((xa * 3u) & ~15u);  // byte offset of tap (x0) inside the staged span
+        const uint32_t woff = off & ~3u, shft = (off & 3u) * 8u;
+        const bool edge = (x1 == x0);
+        const bool fusedp = x < p.fma_bulk;
+        const bool active = x < p.dw;
+        const uint32_t y_first = w.cy * P.rows_per_chunk, y_end = min(y_first + P.rows_per_chunk, p.dh);
+        float* out0 = dst + (size_t)w.img * plane * 3 + (size_t)y_first * p.dw + x;
+        float* out1 = out0 + plane;
+        float* out2 = out1 + plane;
+        for (uint32_t dy = y_first; dy < y_end; ++dy, ++k) {
+            const uint32_t stage = k % FS_STAGES, use = k / FS_STAGES;
+            mbar_wait(&full_bar[stage], use & 1u);
+            if (active) {
+                const uint8_t* rp = smem_raw + (size_t)stage * stage_bytes + woff;
+                const float wy = wy_s[stage];
+                float q0, q1, q2;
+                if (!edge) {
+                    if (fusedp) fs_row<true, false>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
+                    else fs_row<false, false>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
+                } else {
+                    if (fusedp) fs_row<true, true>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
+                    else fs_row<false, true>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
+                }
+                *out0 = q0; *out1 = q1; *out2 = q2;
+            }
+            out0 += p.dw; out1 += p.dw; out2 += p.dw;
+            __syncwarp();
+            if (lane0) mbar_arrive(&empty_bar[stage]);
+        }
+    }
+}
+
+int launch_fused_resize_staged(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch,
+                               bool* handled) {
     *handled = false;
+    const uint32_t row_bytes = p.sw * 3u;
+    // TMA 1-D bulk copies need 16-B aligned rows; very strong downscales have sparse taps (the span would be
+    // mostly unused bytes) and stay on the gather kernel.
+    if ((row_bytes & 15u) || !aligned16(src) || p.scale_x > 6.0f || p.sw < 16u) return KB200_OK;
+    // span bound: x0(last) - x0(first) <= ceil((TW-1)*scale_x) + 1 pixels, + the +1 tap, + 16-B rounding both ends
+    const double span_px = (double)(FS_TW - 1) * (double)p.scale_x + 4.0;
+    uint32_t slot = (uint32_t)(span_px * 3.0) + 32u;
+    slot = (slot + 127u) & ~127u;
+    slot = std::min(slot, (row_bytes + 16u + 127u) & ~127u);  // +16: the 3-word tap read may run 8 B past the span
+    const size_t smem = (size_t)slot * 2 * FS_STAGES;
+    if (smem > 200 * 1024) return KB200_OK;
+    static bool attr_done = false;  // idempotent; a benign race would set the same value twice
+    if (smem > 48 * 1024 && !attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(fused_resize_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    FusedStagedParams P;
+    P.p = p;
+    P.tiles_x = (p.dw + FS_TW - 1) / FS_TW;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (220 * 1024) / (smem + 1024)));
+    const size_t ctas = (size_t)device_info().sm_count * per_sm;
+    // chunk height: enough units for ~16 per CTA (load balance) but at least 8 rows (amortise the x-side)
+    const size_t total_rows = (size_t)p.dh * batch * P.tiles_x;
+    uint32_t rc = (uint32_t)std::max<size_t>(8, total_rows / (ctas * 16));
+    rc = std::min(rc, p.dh);
+    P.rows_per_chunk = rc;
+    P.chunks_y = (p.dh + rc - 1) / rc;
+    const size_t nunits = (size_t)P.tiles_x * P.chunks_y * batch;
+    if (nunits > 0x7FFFFFFFull) return KB200_OK;
+    P.nunits = (uint32_t)nunits;
+    P.slot_bytes = slot;
+    P.row_bytes = row_bytes;
+    const unsigned grid = (unsigned)std::min<size_t>(nunits, ctas);
+    P.dtx = grid % P.tiles_x;
+    const uint32_t g = grid / P.tiles_x;
+    P.dcy = g % P.chunks_y;
+    P.dimg = g / P.chunks_y;
+    fused_resize_staged_kernel<<<grid, FS_THREADS, smem, s>>>(src, dst, P);
+    KB200_TRY(check_launch("fused_resize_staged_kernel"));
+    *handled = true;
     return KB200_OK;
 }
+
 }  // namespace kb200

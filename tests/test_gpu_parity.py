@@ -142,7 +142,10 @@ def test_resize_bilinear_normalize(kb, oracle, dev):
 
 
 FUSED_CASES = [(60, 40, 37, 23), (74, 10, 37, 5), (384, 216, 128, 72), (128, 72, 384, 216), (100, 75, 33, 41), (40, 24, 20, 12),
-               (67, 33, 66, 32), (3840, 24, 1280, 8)]
+               (67, 33, 66, 32), (3840, 24, 1280, 8),
+               # 16-byte-aligned rows: the TMA row-span staged kernel (several x-tiles, ragged last tile, up/down, 1:1-ish)
+               (256, 64, 100, 30), (512, 40, 171, 13), (1024, 30, 1000, 29), (1600, 21, 300, 9), (640, 18, 1279, 35),
+               (1920, 27, 1281, 19), (48, 9, 50, 10), (16, 16, 3, 3)]
 
 
 @pytest.mark.parametrize("sw,sh,dw,dh", FUSED_CASES)
