@@ -26,9 +26,11 @@ __global__ void __launch_bounds__(256) gray_from_rgb_f32_vec4(const float4* __re
                                                               size_t nquads, size_t bulk_px) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
-        const float4 a = ldg_stream_f4(src + 3 * q);      // r0 g0 b0 r1
-        const float4 b = ldg_stream_f4(src + 3 * q + 1);  // g1 b1 r2 g2
-        const float4 c = ldg_stream_f4(src + 3 * q + 2);  // b2 r3 g3 b3
+        // L1-allocating loads: the three vectors of a thread interleave with its neighbours' (48-B lane stride), so the
+        // second and third instruction hit the sectors the first one brought in
+        const float4 a = __ldg(src + 3 * q);      // r0 g0 b0 r1
+        const float4 b = __ldg(src + 3 * q + 1);  // g1 b1 r2 g2
+        const float4 c = __ldg(src + 3 * q + 2);  // b2 r3 g3 b3
         const size_t p = 4 * q;
         float4 o;
         // bulk_px is a multiple of 8, so the 4 px of a quad are all on one side of it.
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(256) gray_from_rgb_u8_vec16(const uint4* __res
                                                               size_t ngroups) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < ngroups; q += stride) {
-        const uint4 A = ldg_stream_u4(src + 3 * q), B = ldg_stream_u4(src + 3 * q + 1), C = ldg_stream_u4(src + 3 * q + 2);
+        const uint4 A = __ldg(src + 3 * q), B = __ldg(src + 3 * q + 1), C = __ldg(src + 3 * q + 2);  // L1-allocating (48-B lane stride)
         const uint32_t w[12] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w, C.x, C.y, C.z, C.w};
         uint32_t out[4];
 #pragma unroll

@@ -128,6 +128,233 @@ __global__ void __launch_bounds__(256) sep_filter_fused_kernel(const float* __re
     }
 }
 
+// ─────────────────────────────────────────────────────────────────────────────────────────────
+// Row-streaming variant (the config-4 fast path): C ∈ {1,3,4}, taps ∈ {3,5,7}, (cols*C) % 4 == 0.
+//
+// ncu on the tile kernel above: ~90 instructions per element (K LDS + 2K FP per pass per element, 64-bit
+// index math in the tap loops), issue-bound at 28 % (blur) / 14 % (sobel) of the HBM roofline.  Here:
+//   * work unit = (image, strip of 512 floats of a row, chunk of `rows_per_chunk` rows); a CTA walks its
+//     strip top-down.  Each input row segment (strip + 16-B-rounded halo) is copied global -> shared by
+//     the TMA engine (cp.async.bulk 1-D) into an 8-deep mbarrier ring by a producer warp — every input
+//     row is read once per chunk (+ K-1 halo rows per chunk), nothing is staged twice horizontally.
+//   * a consumer thread owns ONE float4 column of the strip.  Per row it reads its 4 outputs' horizontal
+//     support as NF4 aligned LDS.128, forms the 4 horizontal results in registers, pushes them into a
+//     K-deep register window (rotation is free: the row loop is unrolled K times) and emits the vertical
+//     result of the row that just became complete with one lane-contiguous STG.128.
+//   * the f32 intermediate never leaves the register file.
+// Zero border: rows outside the image are not copied — the producer just arrives and flags the row, the
+// consumer pushes zeros; float4s left/right of the image row are zeroed in registers (edge strips only).
+// Arithmetic per output is the reference's: acc = 0; acc += v*k in ascending tap order, unfused.
+static constexpr int SS_COLS4 = 128;                // float4 columns per strip = consumer threads
+static constexpr int SS_EW = SS_COLS4 * 4;          // floats per strip
+static constexpr int SS_STAGES = 8;
+static constexpr int SS_THREADS = SS_COLS4 + 32;    // + producer warp
+
+struct SepStreamParams {
+    uint32_t rowlen;       // cols * C floats
+    uint32_t rows, batch;
+    uint32_t strips, chunks, rows_per_chunk, nunits;
+    uint32_t slot_floats;  // floats per stage slot
+};
+
+__device__ __forceinline__ uint32_t ss_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ss_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ss_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ss_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ss_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ss_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ss_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ss_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SS_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SS_WAIT_DONE;\n"
+        "bra SS_WAIT_LOOP;\n"
+        "SS_WAIT_DONE:\n"
+        "}\n" ::"r"(ss_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ss_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ss_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(ss_smem_u32(bar))
+                 : "memory");
+}
+
+template <int C, int KX, int KY, bool SOBEL>
+__global__ void __launch_bounds__(SS_THREADS) sep_filter_stream_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                       const __grid_constant__ SepTaps taps,
+                                                                       const __grid_constant__ SepStreamParams P) {
+    constexpr int HX = KX / 2, HY = KY / 2;
+    constexpr int HL = ((HX * C + 3) / 4) * 4;                 // left halo, floats, 16-B rounded
+    constexpr int HR = (((KX - 1 - HX) * C + 3) / 4) * 4;      // right halo
+    constexpr int NF4 = 1 + HL / 4 + HR / 4;                   // float4s a thread reads per row
+    constexpr int OFF = HL - HX * C;                           // in[] index of tap 0 of output 0
+    extern __shared__ __align__(128) float ss_smem[];
+    __shared__ __align__(8) uint64_t full_bar[SS_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[SS_STAGES];
+    __shared__ int row_valid[SS_STAGES];
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < SS_STAGES; ++s) { ss_mbar_init(&full_bar[s], 1); ss_mbar_init(&empty_bar[s], SS_COLS4 / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t img_floats = (size_t)P.rowlen * P.rows;
+    uint32_t k = 0;  // running staged-row counter: stage = k % STAGES, use = k / STAGES
+
+    if (tid >= SS_COLS4) {
+        if (tid != SS_COLS4) return;
+        // ── producer lane ──
+        for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
+            const uint32_t strip = u % P.strips, rest = u / P.strips;
+            const uint32_t chunk = rest % P.chunks, img = rest / P.chunks;
+            const int e0 = (int)(strip * SS_EW);
+            const int g0 = max(e0 - HL, 0), g1 = min(e0 + SS_EW + HR, (int)P.rowlen);  // floats, multiples of 4
+            const uint32_t bytes = (uint32_t)(g1 - g0) * 4u;
+            const uint32_t slot_off = (uint32_t)(g0 - (e0 - HL));                        // floats into the slot
+            const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
+            const float* base = src + (size_t)img * img_floats + g0;
+            for (int iy = y_first - HY; iy < y_end + (KY - 1 - HY); ++iy, ++k) {
+                const uint32_t stage = k % SS_STAGES, use = k / SS_STAGES;
+                if (use > 0) ss_mbar_wait(&empty_bar[stage], (use - 1u) & 1u);
+                const bool valid = iy >= 0 && iy < (int)P.rows;
+                row_valid[stage] = valid ? 1 : 0;
+                if (valid) {
+                    ss_mbar_expect_tx(&full_bar[stage], bytes);
+                    ss_tma_load_1d(ss_smem + (size_t)stage * P.slot_floats + slot_off, base + (size_t)iy * P.rowlen, bytes, &full_bar[stage]);
+                } else {
+                    ss_mbar_arrive(&full_bar[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ── consumers: one float4 column each ──
+    const bool lane0 = (tid & 31u) == 0;
+    for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
+        const uint32_t strip = u % P.strips, rest = u / P.strips;
+        const uint32_t chunk = rest % P.chunks, img = rest / P.chunks;
+        const int e0 = (int)(strip * SS_EW);
+        const int e = e0 + 4 * (int)tid;                 // first global float of this thread's outputs
+        const bool active = e < (int)P.rowlen;
+        const bool edge_unit = (e0 - HL < 0) || (e0 + SS_EW + HR > (int)P.rowlen);
+        const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
+        float* out = dst + (size_t)img * img_floats + (size_t)y_first * P.rowlen + e;
+        float winA[KY][4], winB[SOBEL ? KY : 1][4];
+#pragma unroll
+        for (int t = 0; t < KY; ++t)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { winA[t][j] = 0.0f; if (SOBEL) winB[t][j] = 0.0f; }
+        int iy = y_first - HY;
+        const int iy_end = y_end + (KY - 1 - HY);
+        while (iy < iy_end) {
+#pragma unroll
+            for (int s = 0; s < KY; ++s) {   // unrolled: window slot indices are compile-time
+                if (iy >= iy_end) break;
+                const uint32_t stage = k % SS_STAGES, use = k / SS_STAGES;
+                ss_mbar_wait(&full_bar[stage], use & 1u);
+                float hA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, hB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (row_valid[stage] && active) {
+                    const float4* sp = reinterpret_cast<const float4*>(ss_smem + (size_t)stage * P.slot_floats) + tid;
+                    float in[NF4 * 4];
+#pragma unroll
+                    for (int q = 0; q < NF4; ++q) {
+                        float4 v = sp[q];
+                        if (edge_unit) {
+                            const int gi = e - HL + 4 * q;   // global float index of this float4
+                            if (gi < 0 || gi >= (int)P.rowlen) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        }
+                        in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float a = 0.0f, b = 0.0f;
+#pragma unroll
+                        for (int t = 0; t < KX; ++t) {
+                            const float v = in[OFF + j + t * C];
+                            a += v * taps.kx[t];
+                            if (SOBEL) b += v * taps.ky[t];
+                        }
+                        hA[j] = a; hB[j] = b;
+                    }
+                }
+                __syncwarp();
+                if (lane0) ss_mbar_arrive(&empty_bar[stage]);
+                ++k;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { winA[s][j] = hA[j]; if (SOBEL) winB[s][j] = hB[j]; }
+                // the row that just became complete: r = iy - (KY-1-HY); its window is slots s+1 … s+KY (mod KY), oldest first
+                const int r = iy - (KY - 1 - HY);
+                if (r >= y_first && active) {
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float acc = 0.0f, acc2 = 0.0f;
+#pragma unroll
+                        for (int t = 0; t < KY; ++t) {
+                            acc += winA[(s + 1 + t) % KY][j] * taps.ky[t];
+                            if (SOBEL) acc2 += winB[(s + 1 + t) % KY][j] * taps.kx[t];
+                        }
+                        o[j] = SOBEL ? sqrtf(acc * acc + acc2 * acc2) : acc;
+                    }
+                    stg_stream_f4(reinterpret_cast<float4*>(out + (size_t)(r - y_first) * P.rowlen), make_float4(o[0], o[1], o[2], o[3]));
+                }
+                ++iy;
+            }
+            // a partial pass through the unrolled body leaves the window rotated: only happens at the end of a unit,
+            // after which the window is re-zeroed — nothing to fix up.
+        }
+    }
+}
+
+template <int C, int KX, int KY, bool SOBEL>
+static int launch_sep_stream(cudaStream_t s, const float* src, float* dst, const SepTaps& taps, uint32_t cols, uint32_t rows,
+                             uint32_t batch) {
+    constexpr int HX = KX / 2;
+    constexpr int HL = ((HX * C + 3) / 4) * 4, HR = (((KX - 1 - HX) * C + 3) / 4) * 4;
+    SepStreamParams P;
+    P.rowlen = cols * C; P.rows = rows; P.batch = batch;
+    P.strips = (P.rowlen + SS_EW - 1) / SS_EW;
+    P.slot_floats = SS_EW + HL + HR;
+    const size_t smem = (size_t)P.slot_floats * 4 * SS_STAGES;
+    const size_t ctas = (size_t)device_info().sm_count * 6;
+    // chunk height: ~12 units per CTA, at least 32 rows so the K-1 halo rows stay a few percent
+    const size_t total = (size_t)P.strips * batch * rows;
+    uint32_t rc = (uint32_t)std::max<size_t>(32, total / (ctas * 12));
+    rc = std::min(rc, rows);
+    P.rows_per_chunk = rc;
+    P.chunks = (rows + rc - 1) / rc;
+    const size_t nunits = (size_t)P.strips * P.chunks * batch;
+    if (nunits > 0x7FFFFFFFull) return fail(KB200_ERR_DIMS_TOO_LARGE, "too many filter work units (%zu)", nunits);
+    P.nunits = (uint32_t)nunits;
+    const unsigned grid = (unsigned)std::min<size_t>(nunits, ctas);
+    sep_filter_stream_kernel<C, KX, KY, SOBEL><<<grid, SS_THREADS, smem, s>>>(src, dst, taps, P);
+    return check_launch("sep_filter_stream_kernel");
+}
+
+// returns true if a streaming instance exists for (C, kx, ky, sobel) and launched it (status in *st)
+static bool try_sep_stream(cudaStream_t s, const float* src, float* dst, const SepTaps& taps, uint32_t cols, uint32_t rows,
+                           uint32_t C, uint32_t batch, bool sobel, int* st) {
+    if (((size_t)cols * C) % 4 != 0 || !aligned16(src) || !aligned16(dst) || (size_t)cols * C < 16) return false;
+    const int kx = taps.kxn, ky = taps.kyn;
+#define KB200_SS_CASE(CC, KK, SB)                                                             \
+    if (C == CC && kx == KK && ky == KK && sobel == SB) {                                     \
+        *st = launch_sep_stream<CC, KK, KK, SB>(s, src, dst, taps, cols, rows, batch);        \
+        return true;                                                                          \
+    }
+    KB200_SS_CASE(3, 5, false) KB200_SS_CASE(3, 3, false) KB200_SS_CASE(3, 7, false)
+    KB200_SS_CASE(1, 5, false) KB200_SS_CASE(1, 3, false) KB200_SS_CASE(1, 7, false)
+    KB200_SS_CASE(4, 5, false) KB200_SS_CASE(4, 3, false)
+    KB200_SS_CASE(3, 3, true) KB200_SS_CASE(3, 5, true) KB200_SS_CASE(1, 3, true) KB200_SS_CASE(1, 5, true)
+#undef KB200_SS_CASE
+    return false;
+}
+
 // cuda/filter.rs:515-530
 __global__ void gradient_magnitude_kernel(const float* __restrict__ gx, const float* __restrict__ gy,
                                           float* __restrict__ dst, size_t n) {
@@ -168,6 +395,10 @@ static int launch_sep(cudaStream_t s, const float* src, size_t src_len, float* d
     for (uint32_t i = 0; i < kxn; ++i) taps.kx[i] = kx[i];
     for (uint32_t i = 0; i < kyn; ++i) taps.ky[i] = ky[i];
     taps.kxn = (int)kxn; taps.kyn = (int)kyn;
+    {
+        int st = KB200_OK;
+        if (try_sep_stream(s, src, dst, taps, cols, rows, C, batch, sobel, &st)) return st;
+    }
     SepGeom g;
     g.cols = cols; g.rows = rows; g.C = C;
     g.tw = 64; g.th = 32;

@@ -14,6 +14,8 @@
 // One exact shortcut: when ax == 0 the x1 taps are multiplied by zero — `t00 + (t10-t00)*0` is t00
 // bit-for-bit for the finite decoded values — so those taps are not fetched (same for ay == 0).  At
 // integer scales (1080p NV12 → 1080p CHW, config 3a) that removes 3 of the 4 decodes per pixel.
+#include <cuda_fp16.h>
+
 #include "kb200_common.cuh"
 
 namespace kb200 {
@@ -137,6 +139,88 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(const __grid_co
     }
 }
 
+// ── NV12 identity fast path (config 3a: 1080p NV12 → [N,3,1080,1920], scale 1, no pad) ─────────────────────
+// When scale_x == scale_y == 1 and pad == 0, sx = (float)ox / 1.0f = ox exactly, so ax = ay = 0 and the
+// bilinear (and the nearest) sample is the decoded tap (ox, oy) itself — bit-for-bit (see the header note).
+// The generic kernel spends ~150 instructions per pixel here and reaches 21 % of the HBM roofline (ncu: issue-
+// bound).  This kernel is a pure streaming decode:
+//   * one thread = 8 luma columns x 2 rows (one chroma row): 3 x LDG.64 in, 12 x STG.128 out (f32) — a warp
+//     reads 256 contiguous bytes per plane row and writes 1 KB contiguous per output plane row;
+//   * the chroma terms (CUB*u+half, CUG*u+CVG*v+half, CVR*v+half) are computed once per 2x2 block;
+//   * `px / 255.0f` for the INTEGER px in [0,255] is evaluated as q = px*c; e = fma(-q,255,px); q' = fma(e,c,q)
+//     with c = RN(1/255): Markstein's correction gives the correctly rounded quotient (verified for all 256
+//     values, tests/test_abi_and_host.py) — identical bits to the IEEE division the reference performs.
+template <bool F16>
+__device__ __forceinline__ void nv12_store4(void* __restrict__ dst, size_t idx, const float v[4]) {
+    if (F16) {
+        unsigned short hbits[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // hardware RNE == the reference's manual RNE for every finite value below the f16 overflow threshold;
+            // beyond it (and for NaN) defer to the reference's own bit rules
+            hbits[i] = (fabsf(v[i]) < 65504.0f) ? __half_as_ushort(__float2half_rn(v[i])) : f2h_ref(v[i]);
+        }
+        uint2 w;
+        w.x = hbits[0] | ((uint32_t)hbits[1] << 16); w.y = hbits[2] | ((uint32_t)hbits[3] << 16);
+        *reinterpret_cast<uint2*>(reinterpret_cast<unsigned short*>(dst) + idx) = w;
+    } else {
+        stg_stream_f4(reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + idx), make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+__device__ __forceinline__ float norm_int_px(int r, float m, float is) {
+    const float c = 0.00392156885936856269836f;  // RN(1/255) = 0x3b808081
+    const float p = (float)r;
+    const float q = p * c;
+    const float e = fmaf(-q, 255.0f, p);
+    const float q2 = fmaf(e, c, q);  // == p / 255.0f for integer p in [0, 255]
+    return (q2 - m) * is;
+}
+
+// One thread = 4 luma columns x 2 rows.  Every warp-level access is lane-contiguous: 3 x LDG.32 (128 B per
+// warp), 6 x STG.128 (512 contiguous bytes per warp per plane row).  [The first version gave each thread 8
+// columns = two STG.128 per plane row; each store instruction then wrote only half of every 32-B sector and
+// ncu showed 2x the write sectors at L2 (lts__t_sectors_srcunit_tex_op_write) with l1tex at 86 %.]
+template <bool F16, bool PTRS>
+__global__ void __launch_bounds__(128) preprocess_nv12_identity_kernel(const __grid_constant__ kb200_preprocess_desc d,
+                                                                       const __grid_constant__ PreFrames fr, void* __restrict__ dst,
+                                                                       uint32_t frame0, uint32_t groups_per_row, uint32_t items) {
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= items) return;
+    const uint32_t rp = item / groups_per_row, g = item - rp * groups_per_row;
+    const uint32_t w = (uint32_t)d.src_w, h = (uint32_t)d.src_h;
+    const uint32_t f = blockIdx.y;
+    const uint8_t* src = PTRS ? fr.ptr[f] : fr.base + (size_t)(frame0 + f) * fr.stride;
+    const uint32_t x = g * 4u;
+    const uint32_t y0w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(2u * rp) * w + x));
+    const uint32_t y1w = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)(2u * rp + 1u) * w + x));
+    const uint32_t uvw = __ldg(reinterpret_cast<const uint32_t*>(src + (size_t)w * h + (size_t)rp * w + x));
+    ChromaTerms ct[2];
+    ct[0] = chroma_terms((int)(uvw & 0xFFu), (int)((uvw >> 8) & 0xFFu));
+    ct[1] = chroma_terms((int)((uvw >> 16) & 0xFFu), (int)(uvw >> 24));
+    const size_t plane = (size_t)w * h;
+    const size_t base = (size_t)(frame0 + f) * 3 * plane + (size_t)(2u * rp) * w + x;
+    const float m0 = d.mean[0], m1 = d.mean[1], m2 = d.mean[2], i0 = d.inv_std[0], i1 = d.inv_std[1], i2 = d.inv_std[2];
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+        const uint32_t yw = row == 0 ? y0w : y1w;
+        float r4[4], g4[4], b4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int yv = (int)((yw >> (8 * i)) & 0xFFu);
+            int r, gg, b;
+            decode_rgb(yy_term(yv), ct[i >> 1], r, gg, b);
+            r4[i] = norm_int_px(r, m0, i0);
+            g4[i] = norm_int_px(gg, m1, i1);
+            b4[i] = norm_int_px(b, m2, i2);
+        }
+        const size_t o = base + (size_t)row * w;
+        nv12_store4<F16>(dst, o, r4);
+        nv12_store4<F16>(dst, o + plane, g4);
+        nv12_store4<F16>(dst, o + 2 * plane, b4);
+    }
+}
+
 static size_t src_bytes(const kb200_preprocess_desc& d) {
     const size_t chroma = d.fmt == KB200_FMT_NV12 ? (size_t)d.src_w * d.src_h / 2 : 0;
     return (size_t)d.src_pitch * d.src_h + chroma;
@@ -167,11 +251,28 @@ static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, con
                              const uint8_t* base, size_t stride, uint32_t batch, void* dst) {
     const int pixels = d.dst_w * d.dst_h;
     const bool bil = d.sampling == KB200_INTERP_BILINEAR;
+    // identity fast path: NV12, scale 1, no pad, same size, 8-column vectors possible
+    bool identity = d.fmt == KB200_FMT_NV12 && d.scale_x == 1.0f && d.scale_y == 1.0f && d.pad_x == 0.0f && d.pad_y == 0.0f &&
+                    d.dst_w == d.src_w && d.dst_h == d.src_h && (d.src_w % 4) == 0 && aligned16(dst);
+    if (identity) {
+        if (frames) { for (uint32_t k = 0; k < batch; ++k) identity = identity && ((reinterpret_cast<uintptr_t>(frames[k]) & 3u) == 0); }
+        else identity = ((reinterpret_cast<uintptr_t>(base) & 3u) == 0) && (stride % 4 == 0);
+    }
+    const uint32_t id_groups = (uint32_t)d.src_w / 4u;
+    const size_t id_items = (size_t)id_groups * ((size_t)d.src_h / 2);
+    if (id_items > 0x7FFFFFFFull) identity = false;
     for (uint32_t f0 = 0; f0 < batch; f0 += 256) {
         const uint32_t nb = std::min<uint32_t>(256, batch - f0);
         PreFrames fr{};
         fr.base = base; fr.stride = stride;
         if (frames) for (uint32_t k = 0; k < nb; ++k) fr.ptr[k] = frames[f0 + k];
+        if (identity) {
+            dim3 grid(div_up(id_items, 128), nb);
+            if (frames) preprocess_nv12_identity_kernel<F16, true><<<grid, 128, 0, s>>>(d, fr, dst, f0, id_groups, (uint32_t)id_items);
+            else preprocess_nv12_identity_kernel<F16, false><<<grid, 128, 0, s>>>(d, fr, dst, f0, id_groups, (uint32_t)id_items);
+            KB200_TRY(check_launch("preprocess_nv12_identity_kernel"));
+            continue;
+        }
         dim3 grid(div_up(pixels, 256), nb);
         if (frames) {
             if (bil) preprocess_generic_kernel<F16, true, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);

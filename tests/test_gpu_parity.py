@@ -563,3 +563,31 @@ def test_interop_dlpack_and_cai(kb, dev):
     assert kb.Image(torch.zeros(2, 2, 3, dtype=torch.uint8, device=dev)).__cuda_array_interface__["typestr"] == "|u1"
     with pytest.raises(AttributeError):
         kb.Image(torch.zeros(2, 2, 3)).__cuda_array_interface__
+
+
+@pytest.mark.parametrize("w,h,n", [(64, 48, 2), (8, 2, 1), (1928, 6, 1), (72, 10, 3), (4, 2, 1), (132, 4, 2)])
+@pytest.mark.parametrize("f16", [False, True])
+def test_preprocess_nv12_identity_fast_path(kb, oracle, dev, w, h, n, f16):
+    """Scale 1 / no pad takes the streaming NV12 kernel: every decoded value 0..255 must normalise to the same bits
+    as the reference's `px / 255.0f` division, in f32 and (RNE) f16, through both frame-addressing modes."""
+    frame = w * h * 3 // 2
+    raws = [oracle.pattern_u8(frame, 0xABCD + k) for k in range(n)]
+    raws[0][:min(frame, 512)] = np.arange(min(frame, 512)) % 256  # every Y value appears
+    for mode in (kb.ResizeMode.Stretch, kb.ResizeMode.Letterbox):
+        pre = (kb.Preprocessor.builder().source_format(kb.SourceFormat.Nv12).mode(mode).normalize(kb.Normalize.imagenet()).build_cuda())
+        dst = torch.zeros((n, 3, h, w), dtype=torch.float16 if f16 else torch.float32, device=dev)
+        frames = [cu(r, dev) for r in raws]
+        (pre.run_raw_batch_f16 if f16 else pre.run_raw_batch)(frames, w, h, dst)
+        inv = tuple(float(np.float32(1.0) / np.float32(s)) for s in kb.IMAGENET_STD)
+        cfg = oracle.PreprocessCfg(mode=oracle.STRETCH, fmt=oracle.FMT_NV12, mean=kb.IMAGENET_MEAN, inv_std=inv)
+        want = np.stack([oracle.preprocess_frame(r, cfg, w, h, w, h, f16=f16) for r in raws])
+        got = dst.cpu().numpy()
+        if f16:
+            np.testing.assert_array_equal(got.view(np.uint16), want.view(np.uint16))
+        else:
+            assert_f32_equal(got, want)
+        # strided addressing of the same frames
+        ring = torch.cat(frames)
+        dst2 = torch.zeros_like(dst)
+        pre.run_raw_strided(ring, frame, n, w, h, dst2, f16=f16)
+        assert torch.equal(dst, dst2)
