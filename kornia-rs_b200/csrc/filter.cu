@@ -184,6 +184,35 @@ __device__ __forceinline__ void ss_tma_load_1d(void* smem_dst, const void* gmem_
                  : "memory");
 }
 
+// Sobel taps are compile-time constants (filter/kernels.rs:55-72): D = derivative, S = smoothing.
+template <int K> struct SobelTaps;
+template <> struct SobelTaps<3> { static constexpr int D[3] = {-1, 0, 1}; static constexpr int S[3] = {1, 2, 1}; };
+template <> struct SobelTaps<5> { static constexpr int D[5] = {-1, -2, 0, 2, 1}; static constexpr int S[5] = {1, 4, 6, 4, 1}; };
+
+// acc + v*k for a compile-time integer tap, bit-identical to the reference's unfused `acc += v * k`:
+//   k == 0      : v*0 = ±0 and acc + ±0 = acc (acc is never -0: every accumulation starts from +0.0) — skipped;
+//   |k| = 2^n   : the product is exact, so one FFMA (single rounding of acc + v*k) equals mul-then-add;
+//   otherwise   : mul, then add.
+// (Finite inputs, like the zero-halo argument in the file header.)
+template <int KV>
+__device__ __forceinline__ float acc_tap(float acc, float v) {
+    if (KV == 0) return acc;
+    if (KV == 1) return acc + v;
+    if (KV == -1) return acc - v;
+    if ((KV & (KV - 1)) == 0 || ((-KV) & (-KV - 1)) == 0) return fmaf(v, (float)KV, acc);
+    return acc + v * (float)KV;
+}
+template <int K, bool DERIV, int T>
+struct SobelAcc {
+    template <typename F>
+    __device__ __forceinline__ static float run(float acc, F&& get) {
+        constexpr int kv = DERIV ? SobelTaps<K>::D[T] : SobelTaps<K>::S[T];
+        acc = acc_tap<kv>(acc, kv == 0 ? 0.0f : get(T));
+        if constexpr (T + 1 < K) return SobelAcc<K, DERIV, T + 1>::run(acc, get);
+        else return acc;
+    }
+};
+
 template <int C, int KX, int KY, bool SOBEL>
 __global__ void __launch_bounds__(SS_THREADS) sep_filter_stream_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                                        const __grid_constant__ SepTaps taps,
@@ -273,14 +302,16 @@ __global__ void __launch_bounds__(SS_THREADS) sep_filter_stream_kernel(const flo
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float a = 0.0f, b = 0.0f;
+                        if constexpr (SOBEL) {
+                            auto get = [&](int t) { return in[OFF + j + t * C]; };
+                            hA[j] = SobelAcc<KX, true, 0>::run(0.0f, get);    // derivative taps along x  (gx)
+                            hB[j] = SobelAcc<KX, false, 0>::run(0.0f, get);   // smoothing taps along x   (gy)
+                        } else {
+                            float a = 0.0f;
 #pragma unroll
-                        for (int t = 0; t < KX; ++t) {
-                            const float v = in[OFF + j + t * C];
-                            a += v * taps.kx[t];
-                            if (SOBEL) b += v * taps.ky[t];
+                            for (int t = 0; t < KX; ++t) a += in[OFF + j + t * C] * taps.kx[t];
+                            hA[j] = a;
                         }
-                        hA[j] = a; hB[j] = b;
                     }
                 }
                 __syncwarp();
@@ -294,13 +325,18 @@ __global__ void __launch_bounds__(SS_THREADS) sep_filter_stream_kernel(const flo
                     float o[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float acc = 0.0f, acc2 = 0.0f;
+                        if constexpr (SOBEL) {
+                            auto getA = [&](int t) { return winA[(s + 1 + t) % KY][j]; };
+                            auto getB = [&](int t) { return winB[(s + 1 + t) % KY][j]; };
+                            const float gx = SobelAcc<KY, false, 0>::run(0.0f, getA);  // smoothing along y
+                            const float gy = SobelAcc<KY, true, 0>::run(0.0f, getB);   // derivative along y
+                            o[j] = sqrtf(gx * gx + gy * gy);
+                        } else {
+                            float acc = 0.0f;
 #pragma unroll
-                        for (int t = 0; t < KY; ++t) {
-                            acc += winA[(s + 1 + t) % KY][j] * taps.ky[t];
-                            if (SOBEL) acc2 += winB[(s + 1 + t) % KY][j] * taps.kx[t];
+                            for (int t = 0; t < KY; ++t) acc += winA[(s + 1 + t) % KY][j] * taps.ky[t];
+                            o[j] = acc;
                         }
-                        o[j] = SOBEL ? sqrtf(acc * acc + acc2 * acc2) : acc;
                     }
                     stg_stream_f4(reinterpret_cast<float4*>(out + (size_t)(r - y_first) * P.rowlen), make_float4(o[0], o[1], o[2], o[3]));
                 }

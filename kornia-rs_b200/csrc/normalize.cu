@@ -152,11 +152,19 @@ __global__ void __launch_bounds__(256) std_mean_kernel(const uint8_t* __restrict
     for (; q < nvec; q += stride) {
         const uint4 v = ldg_stream_u4(v4 + q);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        // byte j of word kk is relative channel (kk + j) % 3.  DP4A does the byte sums: Σ b·sel for the plain sums,
+        // Σ b·(b & mask) for the squares — 3 LOP + 6 IDP4A per word instead of ~20 scalar ops.
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-            s32[j % 3] += b;
-            q32[j % 3] += b * b;
+        for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                uint32_t sel = 0, mask = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((kk + j) % 3 == r) { sel |= 1u << (8 * j); mask |= 0xFFu << (8 * j); }
+                s32[r] = __dp4a(w[kk], sel, s32[r]);
+                q32[r] = __dp4a(w[kk], w[kk] & mask, q32[r]);
+            }
         }
         if (++pending == 8192u) {
 #pragma unroll

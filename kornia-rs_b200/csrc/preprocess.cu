@@ -53,6 +53,16 @@ __device__ __forceinline__ unsigned short f2h_ref(float f) {
     return h;
 }
 
+// `p / 255.0f`, exactly: q = p*c; e = fma(-q, 255, p); q' = fma(e, c, q) with c = RN(1/255) (Markstein's correction).
+// Verified bit-identical to the IEEE division for EVERY float in [0, 256) by kb200_selftest_div255 (1.13e9 inputs,
+// tests/test_gpu_parity.py::test_div255_identity_exhaustive); every px here is a decoded or interpolated value in [0, 255].
+__device__ __forceinline__ float div255_exact(float p) {
+    const float c = 0.00392156885936856269836f;  // 0x3b808081
+    const float q = p * c;
+    const float e = fmaf(-q, 255.0f, p);
+    return fmaf(e, c, q);
+}
+
 __device__ __forceinline__ void yuv_to_rgbf(int yv, int u, int v, float px[3]) {  // :501-508
     const ChromaTerms t = chroma_terms(u, v);
     int r, g, b;
@@ -126,9 +136,12 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(const __grid_co
     } else {
         px[0] = d.pad_value; px[1] = d.pad_value; px[2] = d.pad_value;
     }
-    const float o0 = (__fdiv_rn(px[0], 255.0f) - d.mean[0]) * d.inv_std[0];
-    const float o1 = (__fdiv_rn(px[1], 255.0f) - d.mean[1]) * d.inv_std[1];
-    const float o2 = (__fdiv_rn(px[2], 255.0f) - d.mean[2]) * d.inv_std[2];
+    float q0, q1, q2;
+    if (inside) { q0 = div255_exact(px[0]); q1 = div255_exact(px[1]); q2 = div255_exact(px[2]); }
+    else { q0 = __fdiv_rn(px[0], 255.0f); q1 = q0; q2 = q0; }  // pad_value is caller-supplied: plain IEEE division
+    const float o0 = (q0 - d.mean[0]) * d.inv_std[0];
+    const float o1 = (q1 - d.mean[1]) * d.inv_std[1];
+    const float o2 = (q2 - d.mean[2]) * d.inv_std[2];
     const size_t out = (size_t)(frame0 + f) * 3 * pixels + i;
     if (F16) {
         unsigned short* o = reinterpret_cast<unsigned short*>(dst);
@@ -168,14 +181,7 @@ __device__ __forceinline__ void nv12_store4(void* __restrict__ dst, size_t idx, 
     }
 }
 
-__device__ __forceinline__ float norm_int_px(int r, float m, float is) {
-    const float c = 0.00392156885936856269836f;  // RN(1/255) = 0x3b808081
-    const float p = (float)r;
-    const float q = p * c;
-    const float e = fmaf(-q, 255.0f, p);
-    const float q2 = fmaf(e, c, q);  // == p / 255.0f for integer p in [0, 255]
-    return (q2 - m) * is;
-}
+__device__ __forceinline__ float norm_int_px(int r, float m, float is) { return (div255_exact((float)r) - m) * is; }
 
 // One thread = 4 luma columns x 2 rows.  Every warp-level access is lane-contiguous: 3 x LDG.32 (128 B per
 // warp), 6 x STG.128 (512 contiguous bytes per warp per plane row).  [The first version gave each thread 8
@@ -221,6 +227,124 @@ __global__ void __launch_bounds__(128) preprocess_nv12_identity_kernel(const __g
     }
 }
 
+// ── NV12 general path (config 3b: 1080p NV12 → letterboxed 640x640, and every other NV12 geometry) ──────────
+// ncu on the generic kernel for config 3b: 89 % issue-slot utilisation, ~250 instructions per output pixel (format
+// switch, integer div/mod for (ox, oy), byte-granular everything), DRAM at 20 %.  This kernel is NV12-only:
+//   * one thread = 4 consecutive destination pixels of one row; the row comes from blockIdx.y (no div/mod);
+//     pad rows and pad pixels store a host-precomputed normalised pad value; 3 lane-contiguous STG.128 per thread;
+//   * taps are fetched only when their weight is non-zero (exact, see the header) — at integer scale ratios
+//     (1080p → 640 letterbox is exactly 3:1) that is ONE decode per pixel;
+//   * a pixel that was not interpolated is an integer 0..255, whose `px / 255.0f` is the 3-instruction exact
+//     form (norm_int_px); interpolated pixels use the IEEE division.
+struct Nv12Args {
+    float pad_norm[3];  // ((pad_value / 255) - mean) * inv_std, evaluated on the host in f32
+    uint32_t groups;    // ceil(dst_w / 4)
+};
+
+__device__ __forceinline__ void nv12_tap(const uint8_t* __restrict__ src, int x, int y, int w, int h, int rgb[3]) {
+    const int yv = __ldg(src + (size_t)y * w + x);
+    const uint32_t uv = __ldg(reinterpret_cast<const unsigned short*>(src + (size_t)w * h + (size_t)(y >> 1) * w + (x >> 1) * 2));
+    const ChromaTerms t = chroma_terms((int)(uv & 0xFFu), (int)(uv >> 8));
+    decode_rgb(yy_term(yv), t, rgb[0], rgb[1], rgb[2]);
+}
+
+static constexpr int NV12_ROWS = 8;  // destination rows per thread: the x-side of the sampler is computed once for all of them
+
+template <bool F16, bool BILINEAR, bool PTRS>
+__global__ void __launch_bounds__(128) preprocess_nv12_kernel(const __grid_constant__ kb200_preprocess_desc d,
+                                                              const __grid_constant__ PreFrames fr, const __grid_constant__ Nv12Args na,
+                                                              void* __restrict__ dst, uint32_t frame0) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= na.groups) return;
+    const uint32_t f = blockIdx.z;
+    const int ox0 = (int)g * 4;
+    const int w = d.src_w, h = d.src_h;
+    const uint8_t* src = PTRS ? fr.ptr[f] : fr.base + (size_t)(frame0 + f) * fr.stride;
+    const size_t plane = (size_t)d.dst_w * d.dst_h;
+    // x-side, once: plan_pixel + sample_* coordinate rules (preprocess.rs:437-448, :534-563)
+    int xa[4], xb[4];
+    float ax[4];
+    bool xin[4];
+    bool any_in = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float sx = __fdiv_rn((float)(ox0 + j) - d.pad_x, d.scale_x);
+        xin[j] = !(sx < 0.0f || sx >= (float)w);
+        any_in = any_in || xin[j];
+        if (BILINEAR) {
+            const int x0 = (int)floorf(sx);
+            ax[j] = sx - (float)x0;
+            xb[j] = min(x0 + 1, w - 1);
+            xa[j] = max(x0, 0);
+        } else {
+            xa[j] = min(max((int)roundf(sx), 0), w - 1);
+            xb[j] = xa[j]; ax[j] = 0.0f;
+        }
+    }
+    const int oy_first = (int)blockIdx.y * NV12_ROWS;
+#pragma unroll 1
+    for (int r = 0; r < NV12_ROWS; ++r) {
+        const int oy = oy_first + r;
+        if (oy >= d.dst_h) break;
+        const size_t obase = (size_t)(frame0 + f) * 3 * plane + (size_t)oy * d.dst_w + ox0;
+        float o[3][4];
+        const float sy = __fdiv_rn((float)oy - d.pad_y, d.scale_y);
+        const bool row_in = !(sy < 0.0f || sy >= (float)h);
+        if (!(row_in && any_in)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { o[0][j] = na.pad_norm[0]; o[1][j] = na.pad_norm[1]; o[2][j] = na.pad_norm[2]; }
+        } else {
+            int y0, y1 = 0;
+            float ay = 0.0f;
+            if (BILINEAR) {
+                y0 = (int)floorf(sy);
+                ay = sy - (float)y0;
+                y1 = min(y0 + 1, h - 1);
+                y0 = max(y0, 0);
+            } else {
+                y0 = min(max((int)roundf(sy), 0), h - 1);
+            }
+            const bool need_y = BILINEAR && ay != 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!xin[j]) { o[0][j] = na.pad_norm[0]; o[1][j] = na.pad_norm[1]; o[2][j] = na.pad_norm[2]; continue; }
+                int t00[3];
+                nv12_tap(src, xa[j], y0, w, h, t00);
+                const bool need_x = BILINEAR && ax[j] != 0.0f;
+                float px[3];
+                if (!need_x && !need_y) {  // the sample IS the decoded tap (exact, see header)
+                    px[0] = (float)t00[0]; px[1] = (float)t00[1]; px[2] = (float)t00[2];
+                } else {
+                    int t10[3] = {0, 0, 0}, t01[3] = {0, 0, 0}, t11[3] = {0, 0, 0};
+                    if (need_x) nv12_tap(src, xb[j], y0, w, h, t10);
+                    if (need_y) {
+                        nv12_tap(src, xa[j], y1, w, h, t01);
+                        if (need_x) nv12_tap(src, xb[j], y1, w, h, t11);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float a = (float)t00[c];
+                        const float top = need_x ? a + ((float)t10[c] - a) * ax[j] : a;
+                        if (need_y) {
+                            const float cc = (float)t01[c];
+                            const float bot = need_x ? cc + ((float)t11[c] - cc) * ax[j] : cc;
+                            px[c] = top + (bot - top) * ay;
+                        } else {
+                            px[c] = top;
+                        }
+                    }
+                }
+                o[0][j] = (div255_exact(px[0]) - d.mean[0]) * d.inv_std[0];
+                o[1][j] = (div255_exact(px[1]) - d.mean[1]) * d.inv_std[1];
+                o[2][j] = (div255_exact(px[2]) - d.mean[2]) * d.inv_std[2];
+            }
+        }
+        nv12_store4<F16>(dst, obase, o[0]);
+        nv12_store4<F16>(dst, obase + plane, o[1]);
+        nv12_store4<F16>(dst, obase + 2 * plane, o[2]);
+    }
+}
+
 static size_t src_bytes(const kb200_preprocess_desc& d) {
     const size_t chroma = d.fmt == KB200_FMT_NV12 ? (size_t)d.src_w * d.src_h / 2 : 0;
     return (size_t)d.src_pitch * d.src_h + chroma;
@@ -261,6 +385,11 @@ static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, con
     const uint32_t id_groups = (uint32_t)d.src_w / 4u;
     const size_t id_items = (size_t)id_groups * ((size_t)d.src_h / 2);
     if (id_items > 0x7FFFFFFFull) identity = false;
+    // NV12 general fast path: vector stores need dst_w % 4 == 0 and a 16-B (f32) / 8-B (f16) aligned destination
+    const bool nv12_fast = d.fmt == KB200_FMT_NV12 && (d.dst_w % 4) == 0 && aligned16(dst) && d.dst_h <= 65535 * NV12_ROWS;
+    Nv12Args nv{};
+    nv.groups = (uint32_t)(d.dst_w + 3) / 4u;
+    for (int c = 0; c < 3; ++c) nv.pad_norm[c] = (d.pad_value / 255.0f - d.mean[c]) * d.inv_std[c];  // BODY :610-612 on the host (f32, unfused)
     for (uint32_t f0 = 0; f0 < batch; f0 += 256) {
         const uint32_t nb = std::min<uint32_t>(256, batch - f0);
         PreFrames fr{};
@@ -271,6 +400,15 @@ static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, con
             if (frames) preprocess_nv12_identity_kernel<F16, true><<<grid, 128, 0, s>>>(d, fr, dst, f0, id_groups, (uint32_t)id_items);
             else preprocess_nv12_identity_kernel<F16, false><<<grid, 128, 0, s>>>(d, fr, dst, f0, id_groups, (uint32_t)id_items);
             KB200_TRY(check_launch("preprocess_nv12_identity_kernel"));
+            continue;
+        }
+        if (nv12_fast) {
+            dim3 grid(div_up(nv.groups, 128), div_up((size_t)d.dst_h, NV12_ROWS), nb);
+#define KB200_NV12_LAUNCH(BIL, PT) preprocess_nv12_kernel<F16, BIL, PT><<<grid, 128, 0, s>>>(d, fr, nv, dst, f0)
+            if (bil) { if (frames) KB200_NV12_LAUNCH(true, true); else KB200_NV12_LAUNCH(true, false); }
+            else     { if (frames) KB200_NV12_LAUNCH(false, true); else KB200_NV12_LAUNCH(false, false); }
+#undef KB200_NV12_LAUNCH
+            KB200_TRY(check_launch("preprocess_nv12_kernel"));
             continue;
         }
         dim3 grid(div_up(pixels, 256), nb);
@@ -311,11 +449,36 @@ static int preprocess_entry(kb200_stream_t stream, const kb200_preprocess_desc* 
     return launch_preprocess<F16>(as_stream(stream), *desc, frames, base, stride, batch, dst);
 }
 
+__global__ void selftest_div255_kernel(unsigned long long* mismatches) {
+    const float c = 0.00392156885936856269836f;
+    const uint32_t end = 0x43800000u;  // bits of 256.0f
+    unsigned long long bad = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t bits = blockIdx.x * blockDim.x + threadIdx.x; bits < end; bits += stride) {
+        const float p = __uint_as_float(bits);
+        const float q = p * c;
+        const float e = fmaf(-q, 255.0f, p);
+        const float q2 = fmaf(e, c, q);
+        if (__float_as_uint(q2) != __float_as_uint(__fdiv_rn(p, 255.0f))) ++bad;
+        if (bits + stride < bits) break;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace kb200
 
 using namespace kb200;
 
 extern "C" {
+
+KB200_API int kb200_selftest_div255(kb200_stream_t stream, uint64_t* mismatches_dev) {
+    KB200_TRY(check_ptr("mismatches_dev", mismatches_dev));
+    cudaStream_t s = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(mismatches_dev, 0, sizeof(uint64_t), s);
+    if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    selftest_div255_kernel<<<device_info().sm_count * 8, 256, 0, s>>>(reinterpret_cast<unsigned long long*>(mismatches_dev));
+    return check_launch("selftest_div255_kernel");
+}
 
 KB200_API size_t kb200_preprocess_src_bytes(const kb200_preprocess_desc* desc) { return desc ? src_bytes(*desc) : 0; }
 

@@ -375,7 +375,8 @@ FMTS = {"Nv12": (3, lambda w, h: w * h * 3 // 2), "Yuyv": (4, lambda w, h: w * h
 @pytest.mark.parametrize("fmt", list(FMTS))
 @pytest.mark.parametrize("mode", ["Letterbox", "Stretch"])
 @pytest.mark.parametrize("sampling", ["Bilinear", "Nearest"])
-@pytest.mark.parametrize("geom", [(8, 6, 7, 5), (64, 48, 40, 40), (64, 48, 64, 48), (30, 20, 61, 47), (128, 72, 40, 24)])
+@pytest.mark.parametrize("geom", [(8, 6, 7, 5), (64, 48, 40, 40), (64, 48, 64, 48), (30, 20, 61, 47), (128, 72, 40, 24),
+                                  (96, 54, 32, 32), (32, 24, 64, 48), (192, 108, 64, 36)])
 def test_preprocess_formats(kb, oracle, dev, fmt, mode, sampling, geom):
     w, h, dw, dh = geom
     code, blen = FMTS[fmt]
@@ -591,3 +592,16 @@ def test_preprocess_nv12_identity_fast_path(kb, oracle, dev, w, h, n, f16):
         dst2 = torch.zeros_like(dst)
         pre.run_raw_strided(ring, frame, n, w, h, dst2, f16=f16)
         assert torch.equal(dst, dst2)
+
+
+def test_div255_identity_exhaustive(kb, dev):
+    """The 3-instruction `p/255` (Markstein correction with c = RN(1/255)) equals the IEEE division for EVERY
+    float in [0, 256) — checked exhaustively on the device (1.13e9 inputs)."""
+    from kornia_rs_b200 import _lib
+
+    out = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.set_device(0)
+    assert _lib.lib().kb200_selftest_div255(torch.cuda.current_stream(dev).cuda_stream, out.data_ptr()) == 0
+    torch.cuda.synchronize()
+    print("div255 mismatches:", int(out.item()))
+    assert int(out.item()) == 0
