@@ -336,25 +336,40 @@ KO_API int ko_resize_normalize_u8_to_f32_chw_bilinear(const uint8_t* src, size_t
             const float wy = fy - (float)y0;
             const uint8_t* row0 = src + y0 * src_stride;
             const uint8_t* row1 = src + y1 * src_stride;
-            for (size_t dx = 0; dx < dw; ++dx) {
+            float* out[3] = {dst + y * dw, dst + plane + y * dw, dst + 2 * plane + y * dw};
+            // bulk: the reference's SIMD leaf shape (:414-497 / :320-407) — gather GW pixels' 4x3 corner samples into
+            // stack arrays, then per channel a GW-wide FMA blend (the compiler vectorises the k loop)
+            const size_t GW = (leaf == KO_LEAF_AARCH64_NEON) ? 4 : 8;
+            size_t dx = 0;
+            for (; dx < bulk; dx += GW) {
+                float p00[24], p01[24], p10[24], p11[24];
+                for (size_t k = 0; k < GW; ++k) {
+                    const size_t o0 = x0b[dx + k], o1 = x1b[dx + k];
+                    for (int c = 0; c < 3; ++c) {
+                        p00[c * 8 + k] = (float)row0[o0 + c]; p01[c * 8 + k] = (float)row0[o1 + c];
+                        p10[c * 8 + k] = (float)row1[o0 + c]; p11[c * 8 + k] = (float)row1[o1 + c];
+                    }
+                }
+                for (int c = 0; c < 3; ++c) {
+                    for (size_t k = 0; k < GW; ++k) {  // :475-478  fmadd(sub(b,a), wx, a) …
+                        const float a = p00[c * 8 + k], b = p01[c * 8 + k], cc = p10[c * 8 + k], d = p11[c * 8 + k];
+                        const float top = fmaf(b - a, wx[dx + k], a);
+                        const float bot = fmaf(d - cc, wx[dx + k], cc);
+                        const float val = fmaf(bot - top, wy, top);
+                        out[c][dx + k] = fmaf(val, scale[c], bias[c]);
+                    }
+                }
+            }
+            for (; dx < dw; ++dx) {  // scalar leaf / tail :286-317
                 const size_t o0 = x0b[dx], o1 = x1b[dx];
                 const float w = wx[dx];
                 for (int c = 0; c < 3; ++c) {
                     const float a = (float)row0[o0 + c], b = (float)row0[o1 + c];
                     const float cc = (float)row1[o0 + c], d = (float)row1[o1 + c];
-                    float o;
-                    if (dx < bulk) {  // :475-478  fmadd(sub(b,a), wx, a) …
-                        const float top = fmaf(b - a, w, a);
-                        const float bot = fmaf(d - cc, w, cc);
-                        const float val = fmaf(bot - top, wy, top);
-                        o = fmaf(val, scale[c], bias[c]);
-                    } else {  // :286-317
-                        const float top = a + w * (b - a);
-                        const float bot = cc + w * (d - cc);
-                        const float val = top + wy * (bot - top);
-                        o = val * scale[c] + bias[c];
-                    }
-                    dst[c * plane + y * dw + dx] = o;
+                    const float top = a + w * (b - a);
+                    const float bot = cc + w * (d - cc);
+                    const float val = top + wy * (bot - top);
+                    out[c][dx] = val * scale[c] + bias[c];
                 }
             }
         }

@@ -207,7 +207,7 @@ assert total.tolist() == [int(v) for v in osums]
 assert std == ostd.tolist() and mean == omean.tolist()
 assert kb.dist.max_over_ranks(float(r + 1)) == 2.0 and kb.dist.sum_over_ranks(1.0) == 2.0
 kb.dist.barrier()
-print("rank", r, "ok", sh)
+sys.stdout.write("RANK%dOK %d-%d\n" % (r, sh.start, sh.stop)); sys.stdout.flush()
 """
 
 
@@ -226,4 +226,21 @@ def test_world_size_2_gloo(tmp_path):
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+    assert "RANK0OK 0-3" in r.stdout and "RANK1OK 3-5" in r.stdout, r.stdout
+
+
+def test_cfg3b_algorithmic_bytes(oracle):
+    """SURVEY §8(d) asks for the distinct source bytes of config 3b counted exactly in the oracle.  1080p NV12 →
+    640x640 letterbox is an exact 3:1 decimation (sx = 3·ox, sy = 3·(oy-140) in f32): the reference kernel addresses
+    the 2x2 taps {3ox, 3ox+1} x {3oy', 3oy'+1} of every content pixel (the +1 taps carry weight 0)."""
+    w, h = 1920, 1080
+    raw = ((np.arange(w * h * 3 // 2, dtype=np.int64) * 7 + 13) % 251).astype(np.uint8)
+    cfg = oracle.PreprocessCfg(mode=oracle.LETTERBOX, fmt=oracle.FMT_NV12)
+    assert oracle.preprocess_affine(oracle.LETTERBOX, w, h, 640, 640) == (float(np.float32(640) / np.float32(1920)),) * 2 + (0.0, 140.0)
+    out, touched = oracle.preprocess_frame(raw, cfg, w, h, 640, 640, count_touched=True)
+    # Y: 2 of 3 columns x 2 of 3 rows = 1280 x 720 bytes; UV: every pair of the 360+... rows {(3k)>>1, (3k+1)>>1} = 540 rows x 1920 B
+    assert touched == 1280 * 720 + 1920 * 540 == 1958400      # bench.py's algorithmic source bytes for cfg 3b
+    assert out.shape == (3, 640, 640)
+    # (the CUDA kernel fetches only the weight-carrying tap: 640*360 Y + 640*360*2 UV = 691,200 B — fewer than algorithmic)
+    # config 2: 4/9 of the source is addressed (taps at rows/cols 3d+1, 3d+2)
+    assert oracle.count_touched_resize(3840, 2160, 1280, 720, 1) * 3 == 3840 * 2160 * 3 * 4 // 9
