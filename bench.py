@@ -56,22 +56,36 @@ def measured_peak_gbs() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def lcg_pattern_u8(n: int, seed: int, device):
+class LcgPattern:
     """cuda/color/mod.rs:303-316 pattern_u8 with a per-frame seed, vectorised: the k-th LCG state is
     A_k*seed + C_k (mod 2^32) with A_k = a^k, C_k = c*(1 + a + … + a^(k-1)); int64 cumprod/cumsum wrap mod 2^64,
-    whose low 32 bits are exact mod 2^32."""
+    whose low 32 bits are exact mod 2^32.  A and C do not depend on the seed: computed once, reused per frame."""
+
+    def __init__(self, n: int, device):
+        import torch
+
+        self.n = n
+        self.prefix = torch.tensor([0, 255, 255, 0, 0, 0, 255, 255, 255, 1, 254, 128, 128, 128, 64], dtype=torch.uint8, device=device)[:n]
+        m = max(n - 15, 0)
+        a = torch.full((m,), 1664525, dtype=torch.int64, device=device)
+        self.A = torch.cumprod(a, 0) & 0xFFFFFFFF                                      # a^1 … a^m
+        aprev = torch.cat([torch.ones(1, dtype=torch.int64, device=device), self.A[:-1]]) if m else self.A
+        self.C = (1013904223 * (torch.cumsum(aprev, 0) & 0xFFFFFFFF)) & 0xFFFFFFFF
+        del a, aprev
+
+    def frame(self, seed: int, out):
+        """Writes the pattern for `seed` into the flat uint8 tensor `out` (3 kernel launches)."""
+        out[:len(self.prefix)] = self.prefix
+        if self.n > 15:
+            out[15:] = (((self.A * (seed & 0xFFFFFFFF) + self.C) & 0xFFFFFFFF) >> 24).to(out.dtype)
+
+
+def lcg_pattern_u8(n: int, seed: int, device):
     import torch
 
-    prefix = torch.tensor([0, 255, 255, 0, 0, 0, 255, 255, 255, 1, 254, 128, 128, 128, 64], dtype=torch.uint8, device=device)
-    if n <= 15:
-        return prefix[:n].clone()
-    m = n - 15
-    a = torch.full((m,), 1664525, dtype=torch.int64, device=device)
-    A = torch.cumprod(a, 0) & 0xFFFFFFFF                                  # a^1 … a^m
-    Aprev = torch.cat([torch.ones(1, dtype=torch.int64, device=device), A[:-1]])  # a^0 … a^(m-1)
-    S = torch.cumsum(Aprev, 0) & 0xFFFFFFFF
-    state = (A * (seed & 0xFFFFFFFF) + 1013904223 * S) & 0xFFFFFFFF
-    return torch.cat([prefix, (state >> 24).to(torch.uint8)])
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    LcgPattern(n, device).frame(seed, out)
+    return out
 
 
 class ClockSampler:
@@ -332,8 +346,10 @@ def main() -> None:
     # this rank's shard of the image stream: its own 64-frame batch (weak scaling)
     shard = kb.dist.shard_range(BATCH * n_gpus, rank, n_gpus)
     src = torch.empty((BATCH, SH, SW, 3), dtype=torch.uint8, device=dev)
+    gen = LcgPattern(SW * SH * 3, dev)
     for i in range(BATCH):
-        src[i] = lcg_pattern_u8(SW * SH * 3, 0x12345678 + shard.start + i, dev).reshape(SH, SW, 3)
+        gen.frame(0x12345678 + shard.start + i, src[i].view(-1))
+    del gen
     dst = torch.empty((BATCH, 3, DH, DW), dtype=torch.float32, device=dev)
     fn = lambda: kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(src, DW, DH, scale, bias, out=dst)
 

@@ -244,3 +244,16 @@ def test_cfg3b_algorithmic_bytes(oracle):
     # (the CUDA kernel fetches only the weight-carrying tap: 640*360 Y + 640*360*2 UV = 691,200 B — fewer than algorithmic)
     # config 2: 4/9 of the source is addressed (taps at rows/cols 3d+1, 3d+2)
     assert oracle.count_touched_resize(3840, 2160, 1280, 720, 1) * 3 == 3840 * 2160 * 3 * 4 // 9
+
+
+def test_bench_lcg_pattern_matches_reference_generator(oracle):
+    """bench.py generates the per-frame LCG patterns with torch (vectorised closed form); it must equal the
+    reference's sequential generator (cuda/color/mod.rs:303-316) for any seed."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n, seed in ((7, 1), (15, 2), (16, 0x12345678), (5000, 0x12345678 + 63), (100003, 0xFFFFFFFF)):
+        got = bench.lcg_pattern_u8(n, seed, "cpu").numpy()
+        np.testing.assert_array_equal(got, oracle.pattern_u8(n, seed))
