@@ -46,6 +46,14 @@ def _declare(l: C.CDLL) -> None:
         "kb200_resize_bilinear_normalize_f32_c3": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, fp, i], i),
         "kb200_resize_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, i], i),
         "kb200_resize_normalize_chw_u8_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, fp, i], i),
+        "kb200_resize_row_plan": ([u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)], None),
+        "kb200_resize_normalize_chw_u8_f32_rows": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, fp, i, u32, u32, u32], i),
+        "kb200_host_pipeline_create": ([i, sz, sz, i, C.POINTER(vp)], i),
+        "kb200_host_pipeline_destroy": ([vp], None),
+        "kb200_host_pipeline_last_transfer": ([vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)], i),
+        "kb200_host_register": ([vp, sz], i),
+        "kb200_host_unregister": ([vp], i),
+        "kb200_resize_normalize_chw_u8_f32_host": ([vp, vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, fp, i], i),
         "kb200_resize_bilinear_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32], i),
         "kb200_warp_affine_f32_c3": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, i], i),
         "kb200_warp_perspective_f32_c3": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, i], i),

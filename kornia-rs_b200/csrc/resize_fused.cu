@@ -10,15 +10,9 @@
 #include <algorithm>
 
 #include "kb200_common.cuh"
+#include "resize_fused.cuh"
 
 namespace kb200 {
-
-struct FusedParams {
-    uint32_t sw, sh, dw, dh;
-    float scale_x, scale_y;
-    float scale[3], bias[3];
-    uint32_t fma_bulk;
-};
 
 __device__ __forceinline__ float fused_lerp(float a, float b, float c, float d, float wx, float wy, float sc, float bi,
                                             bool fused) {
@@ -41,7 +35,7 @@ __global__ void __launch_bounds__(256) fused_resize_gather_kernel(const uint8_t*
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= p.dw || y >= p.dh) return;
-    const uint8_t* s = src + (size_t)blockIdx.z * p.sw * p.sh * 3;
+    const uint8_t* s = src + (size_t)blockIdx.z * p.sw * p.src_rows * 3;
     const size_t plane = (size_t)p.dw * p.dh;
     float* d = dst + (size_t)blockIdx.z * plane * 3 + (size_t)y * p.dw + x;
     const bool fused = x < p.fma_bulk;
@@ -59,10 +53,13 @@ __global__ void __launch_bounds__(256) fused_resize_gather_kernel(const uint8_t*
     const float fx = fmaxf(((float)x + 0.5f) * p.scale_x - 0.5f, 0.0f);
     const float fy = fmaxf(((float)y + 0.5f) * p.scale_y - 0.5f, 0.0f);
     const uint32_t x0 = min((uint32_t)fx, p.sw - 1u), y0 = min((uint32_t)fy, p.sh - 1u);
-    const uint32_t x1 = min(x0 + 1u, p.sw - 1u), y1 = min(y0 + 1u, p.sh - 1u);
+    const uint32_t x1 = min(x0 + 1u, p.sw - 1u);
     const float wx = fx - (float)x0, wy = fy - (float)y0;
-    const uint8_t* row0 = s + (size_t)y0 * p.sw * 3;
-    const uint8_t* row1 = s + (size_t)y1 * p.sw * 3;
+    // a zero vertical weight drops the y1 row exactly (see fs_row<SINGLE>): alias it to y0, which a compacted source
+    // (row map) is guaranteed to hold
+    const uint32_t y1 = (wy == 0.0f) ? y0 : min(y0 + 1u, p.sh - 1u);
+    const uint8_t* row0 = s + (size_t)fused_row_slot(p, y0) * p.sw * 3;
+    const uint8_t* row1 = s + (size_t)fused_row_slot(p, y1) * p.sw * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const float a = (float)row0[x0 * 3 + c], b = (float)row0[x1 * 3 + c];
@@ -73,6 +70,56 @@ __global__ void __launch_bounds__(256) fused_resize_gather_kernel(const uint8_t*
 
 int launch_fused_resize_staged(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch,
                                bool* handled);
+
+FusedParams make_fused_params(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, const float scale[3], const float bias[3], int leaf) {
+    FusedParams p;
+    p.sw = sw; p.sh = sh; p.dw = dw; p.dh = dh;
+    p.scale_x = (float)sw / (float)dw;
+    p.scale_y = (float)sh / (float)dh;
+    for (int c = 0; c < 3; ++c) { p.scale[c] = scale[c]; p.bias[c] = bias[c]; }
+    const bool box2x = (sw == 2 * dw && sh == 2 * dh);
+    if (leaf == KB200_LEAF_SCALAR) p.fma_bulk = 0;
+    else if (box2x) p.fma_bulk = dw & ~15u;                          // fused_row_avx2 / fused_row_neon: 16 px per iter
+    else p.fma_bulk = (leaf == KB200_LEAF_X86_AVX2_FMA) ? (dw & ~7u) : (dw & ~3u);  // :448 / :355
+    p.row_p = 1; p.row_f = 0; p.row_k = 1; p.src_rows = sh;
+    return p;
+}
+
+// Which source rows does this vertical geometry tap?  Walks every destination row with the sampler's own f32
+// expression (identical on host and device: mul, add, no contraction) and fits the tapped set to a periodic window
+// "rows y with first <= y mod period < first + keep".  Integer downscales fit exactly (3:1 -> period 3, first 1,
+// keep 1; 4:1 -> period 4, first 1, keep 2); anything else reports the dense map (1, 0, 1).
+void resize_row_plan(uint32_t sh, uint32_t dh, uint32_t* period, uint32_t* first, uint32_t* keep) {
+    *period = 1; *first = 0; *keep = 1;
+    if (dh == 0 || sh % dh != 0) return;
+    const uint32_t P = sh / dh;
+    if (P < 3 || (sh == 2 * dh)) return;
+    const float scale_y = (float)sh / (float)dh;
+    uint32_t lo = P, hi = 0;
+    for (uint32_t d = 0; d < dh; ++d) {
+        const float f = std::max(((float)d + 0.5f) * scale_y - 0.5f, 0.0f);
+        const uint32_t y0 = std::min((uint32_t)f, sh - 1u);
+        const float wy = f - (float)y0;
+        const uint32_t y1 = (wy == 0.0f) ? y0 : std::min(y0 + 1u, sh - 1u);
+        if (y0 / P != d || y1 / P != d) return;  // a tap leaves its own period: no compact window
+        lo = std::min(lo, y0 % P); hi = std::max(hi, y1 % P);
+    }
+    if (hi - lo + 1 >= P) return;
+    *period = P; *first = lo; *keep = hi - lo + 1;
+}
+
+int launch_fused_resize(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch) {
+    const bool box2x = (p.sw == 2 * p.dw && p.sh == 2 * p.dh);
+    if (!box2x) {
+        bool handled = false;
+        KB200_TRY(launch_fused_resize_staged(s, src, dst, p, batch, &handled));
+        if (handled) return KB200_OK;
+    }
+    dim3 block(32, 8), grid(div_up(p.dw, 32), div_up(p.dh, 8), batch);
+    if (box2x) fused_resize_gather_kernel<true><<<grid, block, 0, s>>>(src, dst, p);
+    else fused_resize_gather_kernel<false><<<grid, block, 0, s>>>(src, dst, p);
+    return check_launch("fused_resize_gather_kernel");
+}
 
 }  // namespace kb200
 
@@ -93,25 +140,44 @@ KB200_API int kb200_resize_normalize_chw_u8_f32(kb200_stream_t stream, const uin
     KB200_TRY(check_slice("src", src_len, (size_t)sw * sh * 3 * batch));
     KB200_TRY(check_slice("dst", dst_len, (size_t)dw * dh * 3 * batch));
     if (dw == 0 || dh == 0 || sw == 0 || sh == 0) return KB200_OK;  // resize/fused.rs:184-186: empty is a no-op
-    FusedParams p;
-    p.sw = sw; p.sh = sh; p.dw = dw; p.dh = dh;
-    p.scale_x = (float)sw / (float)dw;
-    p.scale_y = (float)sh / (float)dh;
-    for (int c = 0; c < 3; ++c) { p.scale[c] = scale[c]; p.bias[c] = bias[c]; }
-    const bool box2x = (sw == 2 * dw && sh == 2 * dh);
-    if (leaf == KB200_LEAF_SCALAR) p.fma_bulk = 0;
-    else if (box2x) p.fma_bulk = dw & ~15u;                          // fused_row_avx2 / fused_row_neon: 16 px per iter
-    else p.fma_bulk = (leaf == KB200_LEAF_X86_AVX2_FMA) ? (dw & ~7u) : (dw & ~3u);  // :448 / :355
-    cudaStream_t s = as_stream(stream);
-    if (!box2x) {
-        bool handled = false;
-        KB200_TRY(launch_fused_resize_staged(s, src, dst, p, batch, &handled));
-        if (handled) return KB200_OK;
-    }
-    dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
-    if (box2x) fused_resize_gather_kernel<true><<<grid, block, 0, s>>>(src, dst, p);
-    else fused_resize_gather_kernel<false><<<grid, block, 0, s>>>(src, dst, p);
-    return check_launch("fused_resize_gather_kernel");
+    FusedParams p = make_fused_params(sw, sh, dw, dh, scale, bias, leaf);
+    return launch_fused_resize(as_stream(stream), src, dst, p, batch);
+}
+
+KB200_API int kb200_resize_normalize_chw_u8_f32_rows(kb200_stream_t stream, const uint8_t* src, size_t src_len,
+                                                     float* dst, size_t dst_len, uint32_t sw, uint32_t sh, uint32_t dw,
+                                                     uint32_t dh, uint32_t batch, const float scale[3],
+                                                     const float bias[3], int leaf, uint32_t row_period,
+                                                     uint32_t row_first, uint32_t row_keep) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_ptr("scale", scale)); KB200_TRY(check_ptr("bias", bias));
+    if (leaf < 0 || leaf > 2) return fail(KB200_ERR_INVALID_ARGUMENT, "unknown cpu leaf %d", leaf);
+    if (batch == 0) return fail(KB200_ERR_INVALID_ARGUMENT, "batch must be non-zero");
+    if (batch > 65535u) return fail(KB200_ERR_INVALID_ARGUMENT, "batch %u exceeds 65535 per call", batch);
+    if (dw == 0 || dh == 0 || sw == 0 || sh == 0) return KB200_OK;
+    uint32_t P = 1, F = 0, K = 1;
+    resize_row_plan(sh, dh, &P, &F, &K);
+    if (row_period == 0 || row_keep == 0 || row_first + row_keep > row_period || sh % row_period != 0)
+        return fail(KB200_ERR_INVALID_ARGUMENT, "row map (period %u, first %u, keep %u) is not a partition of %u rows",
+                    row_period, row_first, row_keep, sh);
+    // the supplied map must hold every row this geometry taps: either dense, or exactly the plan
+    const bool dense = (row_first == 0 && row_keep == row_period);
+    if (!dense && !(row_period == P && row_first == F && row_keep == K))
+        return fail(KB200_ERR_INVALID_ARGUMENT, "row map (period %u, first %u, keep %u) does not hold the rows %ux%u -> %ux%u taps (plan: %u, %u, %u)",
+                    row_period, row_first, row_keep, sw, sh, dw, dh, P, F, K);
+    FusedParams p = make_fused_params(sw, sh, dw, dh, scale, bias, leaf);
+    if (!dense) { p.row_p = row_period; p.row_f = row_first; p.row_k = row_keep; p.src_rows = sh / row_period * row_keep; }
+    KB200_TRY(check_slice("src", src_len, (size_t)sw * p.src_rows * 3 * batch));
+    KB200_TRY(check_slice("dst", dst_len, (size_t)dw * dh * 3 * batch));
+    return launch_fused_resize(as_stream(stream), src, dst, p, batch);
+}
+
+KB200_API void kb200_resize_row_plan(uint32_t src_h, uint32_t dst_h, uint32_t* period, uint32_t* first, uint32_t* keep) {
+    uint32_t P = 1, F = 0, K = 1;
+    if (src_h && dst_h) resize_row_plan(src_h, dst_h, &P, &F, &K);
+    if (period) *period = P;
+    if (first) *first = F;
+    if (keep) *keep = K;
 }
 
 }  // extern "C"
@@ -213,15 +279,21 @@ struct UnitWalk {
 };
 
 // One destination row for one destination column out of a staged pair of source-row spans.
-template <bool FUSED_LEAF, bool EDGE>
+// SINGLE: the row's vertical weight is exactly 0 (odd integer downscale, e.g. 2160 -> 720), so the y1 row was never
+// staged.  val = top + 0*(bot - top) == top bit-for-bit for the finite, non-negative `top` bytes produce (a -0 product
+// added to +0 gives +0), and fmaf(bot - top, 0, top) == top likewise — the tap is dropped, not approximated.
+template <bool FUSED_LEAF, bool EDGE, bool SINGLE>
 __device__ __forceinline__ void fs_row(const uint8_t* __restrict__ rp, uint32_t slot_bytes, uint32_t shft, float wx, float wy,
                                        float s0, float s1, float s2, float o0, float o1, float o2, float& q0, float& q1, float& q2) {
     const uint32_t* r0 = reinterpret_cast<const uint32_t*>(rp);
     const uint32_t* r1 = reinterpret_cast<const uint32_t*>(rp + slot_bytes);
     const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
-    const uint32_t c0 = r1[0], c1 = r1[1], c2 = r1[2];
     uint32_t lo0 = __funnelshift_r(a0, a1, shft), hi0 = __funnelshift_r(a1, a2, shft);  // bytes off..off+3 | off+4..off+7
-    uint32_t lo1 = __funnelshift_r(c0, c1, shft), hi1 = __funnelshift_r(c1, c2, shft);
+    uint32_t lo1 = 0, hi1 = 0;
+    if (!SINGLE) {
+        const uint32_t c0 = r1[0], c1 = r1[1], c2 = r1[2];
+        lo1 = __funnelshift_r(c0, c1, shft); hi1 = __funnelshift_r(c1, c2, shft);
+    }
     if (EDGE) {  // right image edge: the +1 tap replicates x0 — bytes 3..5 := bytes 0..2
         hi0 = __byte_perm(lo0, 0, 0x4421); lo0 = __byte_perm(lo0, 0, 0x0210);
         hi1 = __byte_perm(lo1, 0, 0x4421); lo1 = __byte_perm(lo1, 0, 0x0210);
@@ -231,12 +303,17 @@ __device__ __forceinline__ void fs_row(const uint8_t* __restrict__ rp, uint32_t 
     for (int c = 0; c < 3; ++c) {
         // biased floats 2^23 + byte: a = tap(x0,y0), b = tap(x1,y0), c = tap(x0,y1), d = tap(x1,y1)
         const float ab = __uint_as_float(__byte_perm(lo0, 0x4B000000u, 0x7650u + (uint32_t)c));
-        const float cb = __uint_as_float(__byte_perm(lo1, 0x4B000000u, 0x7650u + (uint32_t)c));
         const float bb = __uint_as_float(c == 0 ? __byte_perm(lo0, 0x4B000000u, 0x7653u) : __byte_perm(hi0, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
-        const float db = __uint_as_float(c == 0 ? __byte_perm(lo1, 0x4B000000u, 0x7653u) : __byte_perm(hi1, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
-        const float a = ab - 8388608.0f, cc = cb - 8388608.0f;  // exact
-        const float dba = bb - ab, ddc = db - cb;                 // exact: (2^23+b) - (2^23+a) = b - a
+        const float a = ab - 8388608.0f;  // exact
+        const float dba = bb - ab;        // exact: (2^23+b) - (2^23+a) = b - a
         const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), bi = c == 0 ? o0 : (c == 1 ? o1 : o2);
+        if (SINGLE) {
+            res[c] = FUSED_LEAF ? fmaf(fmaf(dba, wx, a), sc, bi) : (a + wx * dba) * sc + bi;
+            continue;
+        }
+        const float cb = __uint_as_float(__byte_perm(lo1, 0x4B000000u, 0x7650u + (uint32_t)c));
+        const float db = __uint_as_float(c == 0 ? __byte_perm(lo1, 0x4B000000u, 0x7653u) : __byte_perm(hi1, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
+        const float cc = cb - 8388608.0f, ddc = db - cb;
         if (FUSED_LEAF) {  // resize/fused.rs:475-478
             const float top = fmaf(dba, wx, a);
             const float bot = fmaf(ddc, wx, cc);
@@ -260,7 +337,7 @@ __global__ void __launch_bounds__(FS_THREADS) fused_resize_staged_kernel(const u
     const FusedParams& p = P.p;
     const uint32_t tid = threadIdx.x;
     const uint32_t stage_bytes = P.slot_bytes * 2u;
-    const size_t frame_bytes = (size_t)P.row_bytes * p.sh;
+    const size_t frame_bytes = (size_t)P.row_bytes * p.src_rows;
     const size_t plane = (size_t)p.dw * p.dh;
 
     if (tid == 0) {
@@ -295,9 +372,10 @@ __global__ void __launch_bounds__(FS_THREADS) fused_resize_staged_kernel(const u
                 fused_axis(dy, p.scale_y, p.sh, &y0, &y1, &wy);
                 wy_s[stage] = wy;  // before the arrive(release): covered by the consumers' acquire on `full`
                 uint8_t* sbase = smem_raw + (size_t)stage * stage_bytes;
-                mbar_expect_tx(&full_bar[stage], bytes * 2u);
-                tma_load_1d(sbase, frame + (size_t)y0 * P.row_bytes, bytes, &full_bar[stage]);
-                tma_load_1d(sbase + P.slot_bytes, frame + (size_t)y1 * P.row_bytes, bytes, &full_bar[stage]);
+                const bool single = (wy == 0.0f);  // zero vertical weight: the y1 row contributes exactly nothing
+                mbar_expect_tx(&full_bar[stage], single ? bytes : bytes * 2u);
+                tma_load_1d(sbase, frame + (size_t)fused_row_slot(p, y0) * P.row_bytes, bytes, &full_bar[stage]);
+                if (!single) tma_load_1d(sbase + P.slot_bytes, frame + (size_t)fused_row_slot(p, y1) * P.row_bytes, bytes, &full_bar[stage]);
             }
         }
         return;
@@ -331,13 +409,15 @@ __global__ void __launch_bounds__(FS_THREADS) fused_resize_staged_kernel(const u
                 const uint8_t* rp = smem_raw + (size_t)stage * stage_bytes + woff;
                 const float wy = wy_s[stage];
                 float q0, q1, q2;
-                if (!edge) {
-                    if (fusedp) fs_row<true, false>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
-                    else fs_row<false, false>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
+#define KB200_FS_ROW(F, E, S) fs_row<F, E, S>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2)
+                if (wy == 0.0f) {  // CTA-uniform: the producer staged y0 only
+                    if (!edge) { if (fusedp) KB200_FS_ROW(true, false, true); else KB200_FS_ROW(false, false, true); }
+                    else       { if (fusedp) KB200_FS_ROW(true, true, true);  else KB200_FS_ROW(false, true, true); }
                 } else {
-                    if (fusedp) fs_row<true, true>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
-                    else fs_row<false, true>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2);
+                    if (!edge) { if (fusedp) KB200_FS_ROW(true, false, false); else KB200_FS_ROW(false, false, false); }
+                    else       { if (fusedp) KB200_FS_ROW(true, true, false);  else KB200_FS_ROW(false, true, false); }
                 }
+#undef KB200_FS_ROW
                 *out0 = q0; *out1 = q1; *out2 = q2;
             }
             out0 += p.dw; out1 += p.dw; out2 += p.dw;

@@ -125,13 +125,63 @@ class NormalizeParams:
         return NormalizeParams(scale.tolist(), bias.tolist())
 
 
+def resize_row_plan(src_h: int, dst_h: int) -> tuple[int, int, int]:
+    """(period, first, keep): the source rows a vertical geometry taps are those with
+    first <= y % period < first + keep.  (1, 0, 1) = all rows.  kb200_resize_row_plan."""
+    a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    _lib.lib().kb200_resize_row_plan(src_h, dst_h, C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+class HostPipeline:
+    """Staging ring for the host-buffer form of the hot path (kb200_host_pipeline): `depth` streams, each with a device
+    source and destination chunk buffer.  Created once per device; calls only enqueue."""
+
+    def __init__(self, device=None, src_chunk_bytes: int = 96 << 20, dst_chunk_bytes: int = 96 << 20, depth: int = 3):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise ImageError.Cuda("HostPipeline needs a CUDA device")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        h = C.c_void_p()
+        _check(_lib.lib().kb200_host_pipeline_create(self.device.index, src_chunk_bytes, dst_chunk_bytes, depth, C.byref(h)))
+        self._h = h
+        self.depth = depth
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib.lib().kb200_host_pipeline_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def last_transfer(self) -> tuple[int, int]:
+        """(h2d_bytes, d2h_bytes) the last call moved over the link."""
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(_lib.lib().kb200_host_pipeline_last_transfer(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+_default_pipelines: dict[int, HostPipeline] = {}
+
+
+def _pipeline_for(pipeline: HostPipeline | None) -> HostPipeline:
+    if pipeline is not None:
+        return pipeline
+    idx = torch.cuda.current_device()
+    if idx not in _default_pipelines:
+        _default_pipelines[idx] = HostPipeline(torch.device("cuda", idx))
+    return _default_pipelines[idx]
+
+
 def resize_normalize_to_tensor_u8_to_f32_bilinear(src, dst_w: int, dst_h: int, scale, bias, out: torch.Tensor | None = None,
-                                                  leaf: int = DEFAULT_LEAF) -> torch.Tensor:
+                                                  leaf: int = DEFAULT_LEAF, pipeline: HostPipeline | None = None) -> torch.Tensor:
     """resize/fused.rs:147 — u8 HWC (or NHWC) → f32 CHW ([N,3,dst_h,dst_w]) bilinear (half-pixel, non-AA)
-    resize + `sample*scale[c] + bias[c]`; exact 2x dispatches to the box average (fused.rs:181-183)."""
+    resize + `sample*scale[c] + bias[c]`; exact 2x dispatches to the box average (fused.rs:181-183).
+
+    Device images run the kernel in place.  HOST images (the reference operator's own signature) go through a
+    `HostPipeline`: chunked upload → kernel → download on the GPU, enqueued on the current stream of the pipeline's
+    device — synchronise that stream before reading `out`.  There is no CPU implementation."""
     t = src.data if isinstance(src, Image) else src
-    if not t.is_cuda:
-        raise ImageError.HostPathNotBuilt("resize_normalize_to_tensor_u8_to_f32_bilinear")
     if t.dtype != torch.uint8:
         raise ImageError.DtypeMismatch(torch.uint8, t.dtype)
     if not t.is_contiguous():
@@ -141,6 +191,20 @@ def resize_normalize_to_tensor_u8_to_f32_bilinear(src, dst_w: int, dst_h: int, s
     n, sh, sw, c = t.shape
     if c != 3:
         raise ImageError.InvalidChannelShape(t.numel(), n * sh * sw * 3)
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise ImageError.HostPathNotBuilt("resize_normalize_to_tensor_u8_to_f32_bilinear")
+        if out is None:
+            out = torch.empty((n, 3, dst_h, dst_w), dtype=torch.float32, pin_memory=True)
+        elif out.is_cuda:
+            raise ImageError.MixedResidency()
+        if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != n * 3 * dst_h * dst_w:
+            raise ImageError.InvalidChannelShape(out.numel(), n * 3 * dst_h * dst_w)
+        pipe = _pipeline_for(pipeline)
+        _lib.set_device(pipe.device.index)
+        _check(_lib.lib().kb200_resize_normalize_chw_u8_f32_host(pipe._h, _stream(pipe.device), t.data_ptr(), t.numel(), out.data_ptr(),
+                                                                out.numel(), sw, sh, dst_w, dst_h, n, _lib.f3(scale), _lib.f3(bias), leaf))
+        return out
     if out is None:
         out = torch.empty((n, 3, dst_h, dst_w), dtype=torch.float32, device=t.device)
     else:
@@ -152,6 +216,26 @@ def resize_normalize_to_tensor_u8_to_f32_bilinear(src, dst_w: int, dst_h: int, s
     _lib.set_device(dev.index)
     _check(_lib.lib().kb200_resize_normalize_chw_u8_f32(_stream(dev), t.data_ptr(), t.numel(), out.data_ptr(), out.numel(),
                                                        sw, sh, dst_w, dst_h, n, _lib.f3(scale), _lib.f3(bias), leaf))
+    return out
+
+
+def resize_normalize_rows(src_rows: torch.Tensor, src_w: int, src_h: int, dst_w: int, dst_h: int, scale, bias, row_map: tuple[int, int, int],
+                          out: torch.Tensor | None = None, leaf: int = DEFAULT_LEAF) -> torch.Tensor:
+    """kb200_resize_normalize_chw_u8_f32_rows — same operator over a row-compacted device source
+    ([N, src_h/period*keep, src_w, 3] u8), bit-identical to the full-image call."""
+    t = src_rows
+    if not t.is_cuda:
+        raise ImageError.HostPathNotBuilt("resize_normalize_rows")
+    if t.dtype != torch.uint8:
+        raise ImageError.DtypeMismatch(torch.uint8, t.dtype)
+    if not t.is_contiguous():
+        raise ImageError.ImageDataNotContiguous()
+    n = t.shape[0]
+    if out is None:
+        out = torch.empty((n, 3, dst_h, dst_w), dtype=torch.float32, device=t.device)
+    _lib.set_device(t.device.index)
+    _check(_lib.lib().kb200_resize_normalize_chw_u8_f32_rows(_stream(t.device), t.data_ptr(), t.numel(), out.data_ptr(), out.numel(), src_w, src_h,
+                                                            dst_w, dst_h, n, _lib.f3(scale), _lib.f3(bias), leaf, *row_map))
     return out
 
 

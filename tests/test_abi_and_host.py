@@ -257,3 +257,29 @@ def test_bench_lcg_pattern_matches_reference_generator(oracle):
     for n, seed in ((7, 1), (15, 2), (16, 0x12345678), (5000, 0x12345678 + 63), (100003, 0xFFFFFFFF)):
         got = bench.lcg_pattern_u8(n, seed, "cpu").numpy()
         np.testing.assert_array_equal(got, oracle.pattern_u8(n, seed))
+
+
+def test_resize_row_plan_matches_tapped_rows(kb):
+    """kb200_resize_row_plan (host-only) reports a window that holds every row the f32 half-pixel sampler taps with a
+    non-zero weight, and is minimal for integer downscales."""
+    import numpy as np
+
+    plan = kb.imgproc.resize_row_plan
+
+    assert plan(2160, 720) == (3, 1, 1)      # BASELINE config 2: wy == 0 on every row
+    assert plan(2160, 540) == (4, 1, 2)
+    assert plan(100, 20) == (5, 2, 1)
+    assert plan(216, 36) == (6, 2, 2)
+    assert plan(2160, 1080) == (1, 0, 1)     # exact 2x is the box path: all rows
+    assert plan(1080, 720) == (1, 0, 1)
+    assert plan(720, 2160) == (1, 0, 1)
+    assert plan(0, 0) == (1, 0, 1)
+    for sh, dh in [(2160, 720), (2160, 540), (100, 20), (216, 36), (63, 21), (45, 9), (1080, 720), (75, 41)]:
+        P, F, K = plan(sh, dh)
+        d = np.arange(dh, dtype=np.float32)
+        f = np.maximum((d + np.float32(0.5)) * (np.float32(sh) / np.float32(dh)) - np.float32(0.5), np.float32(0))
+        y0 = np.minimum(f.astype(np.uint32), sh - 1)
+        wy = f - y0.astype(np.float32)
+        y1 = np.where(wy == 0, y0, np.minimum(y0 + 1, sh - 1))
+        for y in np.concatenate([y0, y1]):
+            assert F <= int(y) % P < F + K, (sh, dh, int(y), (P, F, K))

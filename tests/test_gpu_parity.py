@@ -145,7 +145,9 @@ FUSED_CASES = [(60, 40, 37, 23), (74, 10, 37, 5), (384, 216, 128, 72), (128, 72,
                (67, 33, 66, 32), (3840, 24, 1280, 8),
                # 16-byte-aligned rows: the TMA row-span staged kernel (several x-tiles, ragged last tile, up/down, 1:1-ish)
                (256, 64, 100, 30), (512, 40, 171, 13), (1024, 30, 1000, 29), (1600, 21, 300, 9), (640, 18, 1279, 35),
-               (1920, 27, 1281, 19), (48, 9, 50, 10), (16, 16, 3, 3)]
+               (1920, 27, 1281, 19), (48, 9, 50, 10), (16, 16, 3, 3),
+               # integer downscales: odd ratios have a vertical weight of exactly 0 (single-row staging), even ones 0.5
+               (160, 45, 32, 9), (320, 35, 64, 5), (256, 64, 64, 16), (96, 63, 80, 21), (768, 36, 256, 9), (1280, 30, 1280, 10)]
 
 
 @pytest.mark.parametrize("sw,sh,dw,dh", FUSED_CASES)
@@ -156,6 +158,64 @@ def test_fused_resize_normalize_chw(kb, oracle, dev, sw, sh, dw, dh, leaf):
     out = kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(cu(src, dev), dw, dh, scale, bias, leaf=leaf)
     want = oracle.resize_normalize_u8_to_f32_chw(src, dw, dh, scale, bias, leaf)
     assert_f32_equal(out.cpu().numpy()[0], want, f"fused {sw}x{sh}->{dw}x{dh} leaf={leaf}")
+
+
+ROW_CASES = [(384, 216, 128, 72), (160, 45, 32, 9), (256, 64, 64, 16), (96, 63, 80, 21), (1280, 30, 1280, 10), (60, 40, 37, 23), (64, 32, 32, 16)]
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", ROW_CASES)
+def test_fused_resize_row_compacted_source(kb, oracle, dev, sw, sh, dw, dh):
+    """kb200_resize_normalize_chw_u8_f32_rows over only the rows the geometry taps == the full-image result == oracle."""
+    n = 3
+    src = np.stack([oracle.pattern_u8(sw * sh * 3, 0xBEEF + i).reshape(sh, sw, 3) for i in range(n)])
+    scale, bias = oracle.normalize_params_from_mean_std([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    P, F, K = kb.imgproc.resize_row_plan(sh, dh)
+    assert sh % P == 0 and F + K <= P
+    keep = np.array([y for y in range(sh) if F <= y % P < F + K])
+    compact = np.ascontiguousarray(src[:, keep])
+    assert compact.shape[1] == sh // P * K
+    for leaf in (0, 1, 2):
+        want = np.stack([oracle.resize_normalize_u8_to_f32_chw(src[i], dw, dh, scale, bias, leaf) for i in range(n)])
+        got = kb.imgproc.resize_normalize_rows(cu(compact, dev), sw, sh, dw, dh, scale, bias, (P, F, K), leaf=leaf)
+        assert_f32_equal(got.cpu().numpy(), want, f"rows {sw}x{sh}->{dw}x{dh} map={(P, F, K)} leaf={leaf}")
+    # the dense map is always accepted; a map that drops tapped rows is rejected
+    full = kb.imgproc.resize_normalize_rows(cu(src, dev), sw, sh, dw, dh, scale, bias, (1, 0, 1))
+    assert_f32_equal(full.cpu().numpy(), np.stack([oracle.resize_normalize_u8_to_f32_chw(src[i], dw, dh, scale, bias) for i in range(n)]))
+    if (P, F, K) == (1, 0, 1) and sh % 2 == 0:
+        with pytest.raises(kb.ImageError, match="row map"):
+            kb.imgproc.resize_normalize_rows(cu(src[:, ::2].copy(), dev), sw, sh, dw, dh, scale, bias, (2, 0, 1))
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(384, 216, 128, 72), (256, 64, 64, 16), (100, 75, 33, 41), (40, 24, 20, 12), (512, 40, 171, 13)])
+@pytest.mark.parametrize("pinned", [True, False])
+def test_fused_resize_host_pipeline(kb, oracle, dev, sw, sh, dw, dh, pinned):
+    """Host images in, host tensor out (the reference operator's own signature) through the staging ring: small
+    staging buffers force several chunks per stream, a ragged last chunk and ring wrap-around."""
+    n = 11
+    src = np.stack([oracle.pattern_u8(sw * sh * 3, 0xC0FFEE + i).reshape(sh, sw, 3) for i in range(n)])
+    scale, bias = oracle.normalize_params_from_mean_std([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    want = np.stack([oracle.resize_normalize_u8_to_f32_chw(src[i], dw, dh, scale, bias) for i in range(n)])
+    P, F, K = kb.imgproc.resize_row_plan(sh, dh)
+    frame_up = sw * 3 * (sh // P * K)
+    pipe = kb.imgproc.HostPipeline(dev, src_chunk_bytes=2 * sw * sh * 3 + 7, dst_chunk_bytes=3 * dw * dh * 12, depth=2)
+    hs = torch.from_numpy(src)
+    hd = torch.zeros((n, 3, dh, dw), dtype=torch.float32)
+    if pinned:
+        hs, hd = hs.pin_memory(), hd.pin_memory()
+    with torch.cuda.device(dev):
+        for _ in range(2):  # second call reuses the ring while nothing is in flight
+            hd.zero_()
+            out = kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(hs, dw, dh, scale, bias, out=hd, pipeline=pipe)
+            torch.cuda.current_stream().synchronize()
+            assert out is hd
+            assert_f32_equal(hd.numpy(), want, f"host pipeline {sw}x{sh}->{dw}x{dh}")
+    up, down = pipe.last_transfer()
+    assert up == n * frame_up and down == n * dw * dh * 12
+    # staging smaller than one frame is an argument error, not a crash
+    tiny = kb.imgproc.HostPipeline(dev, src_chunk_bytes=256, dst_chunk_bytes=256, depth=1)
+    with torch.cuda.device(dev), pytest.raises(kb.ImageError, match="smaller than one frame"):
+        kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(hs, dw, dh, scale, bias, out=hd, pipeline=tiny)
+    pipe.close(); tiny.close()
 
 
 def test_fused_resize_batched_unit_scale(kb, oracle, dev):
