@@ -320,6 +320,7 @@ def main() -> None:
     ap.add_argument("--no-ops", action="store_true", help="skip the per-op table")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline sample")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer (e2e) leg; the line then has e2e = null")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -385,39 +386,48 @@ def main() -> None:
         except Exception:
             traffic = None
 
-    # e2e: the operator called with HOST (pinned) images and a host output tensor — kb200_resize_normalize_chw_u8_f32_host:
-    # per step, upload -> kernel -> download of the whole batch inside the timed region, chunked over a 3-stream ring.
-    chunk, nstreams = 8, 3
-    host_src = torch.empty((BATCH, SH, SW, 3), dtype=torch.uint8, pin_memory=True)
-    host_src.copy_(src)
-    host_dst = torch.empty((BATCH, 3, DH, DW), dtype=torch.float32, pin_memory=True)
-    pipe = kb.imgproc.HostPipeline(dev, src_chunk_bytes=chunk * SW * SH * 3, dst_chunk_bytes=chunk * 3 * DW * DH * 4, depth=nstreams)
-
-    def e2e_step():
-        kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(host_src, DW, DH, scale, bias, out=host_dst, pipeline=pipe)
-
-    e2e_steps = max(2, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize()
-    kb.dist.barrier(dev)
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record(st)
-    for _ in range(e2e_steps):
-        e2e_step()
-    s1.record(st)
-    torch.cuda.synchronize()
-    kb.dist.barrier(dev)
-    e2e_ms = kb.dist.max_over_ranks(s0.elapsed_time(s1), dev) / e2e_steps
-    e2e_value = dst_mpix_step / (e2e_ms * 1e-3)
+    e2e = None
     t_wall1 = time.time()
+    if not args.no_e2e:
+        # e2e: the operator called with HOST (pinned) images and a host output tensor — kb200_resize_normalize_chw_u8_f32_host:
+        # per step, upload -> kernel -> download of the whole batch inside the timed region, chunked over a 3-stream ring.
+        chunk, nstreams = 8, 3
+        host_src = torch.empty((BATCH, SH, SW, 3), dtype=torch.uint8, pin_memory=True)
+        host_src.copy_(src)
+        host_dst = torch.empty((BATCH, 3, DH, DW), dtype=torch.float32, pin_memory=True)
+        pipe = kb.imgproc.HostPipeline(dev, src_chunk_bytes=chunk * SW * SH * 3, dst_chunk_bytes=chunk * 3 * DW * DH * 4, depth=nstreams)
+
+        def e2e_step():
+            kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(host_src, DW, DH, scale, bias, out=host_dst, pipeline=pipe)
+
+        e2e_steps = max(2, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        kb.dist.barrier(dev)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(st)
+        for _ in range(e2e_steps):
+            e2e_step()
+        s1.record(st)
+        torch.cuda.synchronize()
+        kb.dist.barrier(dev)
+        e2e_ms = kb.dist.max_over_ranks(s0.elapsed_time(s1), dev) / e2e_steps
+        e2e_value = dst_mpix_step / (e2e_ms * 1e-3)
+        t_wall1 = time.time()
+        # spot-check: the e2e result equals the device-resident result
+        same = bool(torch.equal(host_dst.to(dev), dst))
+        h2d_step, d2h_step = pipe.last_transfer()
+        row_map = kb.imgproc.resize_row_plan(SH, DH)
+        pipe.close()
+        del host_src, host_dst
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+               "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_result": same,
+               "host_src_bytes_per_step": BATCH * SW * SH * 3, "row_map": list(row_map),
+               "how": f"kb200_resize_normalize_chw_u8_f32_host on pinned host buffers: chunks of <= {chunk} frames over a {nstreams}-stream ring "
+                      f"(strided upload of the tapped source rows only — period/first/keep = {row_map} — kernel, download)"}
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    # spot-check: the e2e result equals the device-resident result
-    same = bool(torch.equal(host_dst.to(dev), dst))
-    h2d_step, d2h_step = pipe.last_transfer()
-    row_map = kb.imgproc.resize_row_plan(SH, DH)
-    pipe.close()
-    del host_src, host_dst, src, dst
+    del src, dst
 
     ops = None
     if rank == 0 and not args.no_ops and n_gpus == 1:
@@ -439,11 +449,7 @@ def main() -> None:
             "config": {"workload": WORKLOAD, "global_batch": BATCH * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, no data-path collective)",
                        "l2": "inputs larger than L2: each step walks a 1.59 GB source batch (0.53 GB of tapped rows read) + 0.71 GB destination",
                        "leaf": "x86 AVX2+FMA leaf of the reference (bit-identical)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
-                    "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_result": same,
-                    "host_src_bytes_per_step": BATCH * SW * SH * 3, "row_map": list(row_map),
-                    "how": f"kb200_resize_normalize_chw_u8_f32_host on pinned host buffers: chunks of <= {chunk} frames over a {nstreams}-stream ring "
-                           f"(strided upload of the tapped source rows only — period/first/keep = {row_map} — kernel, download)"},
+            "e2e": e2e,
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "fused_resize (resize_fused.cu)",

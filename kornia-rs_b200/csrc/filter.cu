@@ -19,6 +19,10 @@
 // from finite Gaussian/Sobel tables.)
 #include <algorithm>
 
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+
 #include "kb200_common.cuh"
 
 namespace kb200 {
@@ -129,26 +133,23 @@ __global__ void __launch_bounds__(256) sep_filter_fused_kernel(const float* __re
 }
 
 // ─────────────────────────────────────────────────────────────────────────────────────────────
-// Row-streaming variant (the config-4 fast path): C ∈ {1,3,4}, taps ∈ {3,5,7}, (cols*C) % 4 == 0.
+// Row-streaming kernel (the config-4 fast path): C ∈ {1,3,4}, taps ∈ {3,5,7}, (cols*C) % 4 == 0.
 //
 // ncu on the tile kernel above: ~90 instructions per element (K LDS + 2K FP per pass per element, 64-bit
 // index math in the tap loops), issue-bound at 28 % (blur) / 14 % (sobel) of the HBM roofline.  Here:
-//   * work unit = (image, strip of 512 floats of a row, chunk of `rows_per_chunk` rows); a CTA walks its
+//   * work unit = (image, strip of 512*NV floats of a row, chunk of `rows_per_chunk` rows); a CTA walks its
 //     strip top-down.  Each input row segment (strip + 16-B-rounded halo) is copied global -> shared by
-//     the TMA engine (cp.async.bulk 1-D) into an 8-deep mbarrier ring by a producer warp — every input
-//     row is read once per chunk (+ K-1 halo rows per chunk), nothing is staged twice horizontally.
-//   * a consumer thread owns ONE float4 column of the strip.  Per row it reads its 4 outputs' horizontal
-//     support as NF4 aligned LDS.128, forms the 4 horizontal results in registers, pushes them into a
-//     K-deep register window (rotation is free: the row loop is unrolled K times) and emits the vertical
-//     result of the row that just became complete with one lane-contiguous STG.128.
+//     the TMA engine (cp.async.bulk 1-D) into an mbarrier ring by a producer warp — every input row is
+//     read once per chunk (+ K-1 halo rows per chunk), nothing is staged twice horizontally.
+//   * a consumer thread owns NV float4 columns of the strip (tid, tid+128, …; each lane-contiguous).  Per row it
+//     reads its outputs' horizontal support as NF4 aligned LDS.128, forms the horizontal results in registers,
+//     pushes them into a K-deep register window (rotation is free: the row loop is unrolled K times) and emits
+//     the vertical result of the row that just became complete with lane-contiguous STG.128.
 //   * the f32 intermediate never leaves the register file.
 // Zero border: rows outside the image are not copied — the producer just arrives and flags the row, the
-// consumer pushes zeros; float4s left/right of the image row are zeroed in registers (edge strips only).
+// consumer pushes zeros; float4s left/right of the image row are zeroed in registers (edge strips only; interior
+// strips run a copy of the row loop with no bounds logic).
 // Arithmetic per output is the reference's: acc = 0; acc += v*k in ascending tap order, unfused.
-static constexpr int SS_COLS4 = 128;                // float4 columns per strip = consumer threads
-static constexpr int SS_EW = SS_COLS4 * 4;          // floats per strip
-static constexpr int SS_STAGES = 8;
-static constexpr int SS_THREADS = SS_COLS4 + 32;    // + producer warp
 
 struct SepStreamParams {
     uint32_t rowlen;       // cols * C floats
@@ -213,43 +214,103 @@ struct SobelAcc {
     }
 };
 
-template <int C, int KX, int KY, bool SOBEL>
-__global__ void __launch_bounds__(SS_THREADS) sep_filter_stream_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                                                       const __grid_constant__ SepTaps taps,
-                                                                       const __grid_constant__ SepStreamParams P) {
+// ─────────────────────────────────────────────────────────────────────────────────────────────
+// Packed (f32x2) vertical pass.
+//
+// ncu history (profiles/r1_filters.md): the first streaming kernel (one float4 per thread, scalar mul+add in both
+// passes, bounds selects in every row) ran 47 warp-instructions per output value at 79 % issue utilisation — 35 %
+// unfused FMUL/FADD, ~25 % mbarrier spin — i.e. issue-bound at 0.75 (blur) / 0.69 (sobel) of the HBM roofline.
+//   * the vertical pass runs on register PAIRS with FFMA2 (sm_100 packed fp32: same lane rate as FFMA — measured
+//     126 vs 118 element-updates/clk/SM, tools/scratch/ffma2_probe.cu — at half the issue slots).  The reference's
+//     unfused `acc += v * k` is kept bit-for-bit: ptxas contracts mul.f32x2 + add.f32x2 into one FFMA2 even under
+//     --fmad=false, so the product is formed as fma2(v, k, -0) and the sum as fma2(p, 1, acc) with -0 and 1 passed
+//     as kernel arguments (opaque to the optimiser): two FFMA2 per tap-pair, each rounding once, = mul then add;
+//   * the first tap of every accumulation is a single fma(v, k, +0) (== round(v*k) + 0, signed zeros included);
+//   * the horizontal pass stays scalar: with C = 3 the tap pairs of neighbouring outputs alternate between even
+//     and odd register offsets, and an unaligned pair costs more moves than the packed op saves;
+//   * NV = 1 is what ships: two columns per thread (NV = 2) halve the per-row bookkeeping but need 77-93 registers,
+//     which caps the SM at 4 CTAs / 20 warps and measured 6 % slower than NV = 1 at 6-7 CTAs (56 registers).
+template <int NV> struct SS2 {
+    static constexpr int COLS4 = 128;               // consumer threads
+    static constexpr int EW = COLS4 * 4 * NV;       // floats per strip
+    static constexpr int THREADS = COLS4 + 32;
+    static constexpr int MAX_STAGES = 12;
+};
+
+typedef unsigned long long ss_u64;
+__device__ __forceinline__ ss_u64 ss_pack(float a, float b) { ss_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void ss_unpack(ss_u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ ss_u64 ss_fma2(ss_u64 a, ss_u64 b, ss_u64 c) { ss_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// exact two-rounding helpers on pairs (see header): NZ = (-0,-0), ONE = (1,1), both opaque run-time values
+struct PairConst { ss_u64 nz, one, zero; };
+__device__ __forceinline__ ss_u64 pair_mul(ss_u64 v, ss_u64 k, const PairConst& c) { return ss_fma2(v, k, c.nz); }
+__device__ __forceinline__ ss_u64 pair_add(ss_u64 a, ss_u64 b, const PairConst& c) { return ss_fma2(b, c.one, a); }
+
+// acc + v*k on pairs for a compile-time integer tap (same case analysis as acc_tap above)
+template <int KV>
+__device__ __forceinline__ ss_u64 pair_acc_tap(ss_u64 acc, ss_u64 v, const PairConst& c) {
+    if (KV == 0) return acc;
+    if ((KV & (KV - 1)) == 0 || ((-KV) & (-KV - 1)) == 0) return ss_fma2(v, ss_pack((float)KV, (float)KV), acc);  // exact product: one rounding == two
+    return pair_add(acc, pair_mul(v, ss_pack((float)KV, (float)KV), c), c);
+}
+template <int K, bool DERIV, int T>
+struct SobelAccPair {
+    template <typename F>
+    __device__ __forceinline__ static ss_u64 run(ss_u64 acc, const PairConst& c, F&& get) {
+        constexpr int kv = DERIV ? SobelTaps<K>::D[T] : SobelTaps<K>::S[T];
+        if constexpr (kv != 0) acc = pair_acc_tap<kv>(acc, get(T), c);
+        if constexpr (T + 1 < K) return SobelAccPair<K, DERIV, T + 1>::run(acc, c, get);
+        else return acc;
+    }
+};
+
+struct SepStream2Params {
+    SepStreamParams g;
+    uint32_t stages;
+    float neg_zero, one;   // -0.0f and 1.0f, passed at run time on purpose (see header)
+};
+
+template <int C, int KX, int KY, bool SOBEL, int NV>
+__global__ void __launch_bounds__(SS2<NV>::THREADS) sep_filter_stream2_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                                              const __grid_constant__ SepTaps taps,
+                                                                              const __grid_constant__ SepStream2Params R) {
+    using G = SS2<NV>;
     constexpr int HX = KX / 2, HY = KY / 2;
     constexpr int HL = ((HX * C + 3) / 4) * 4;                 // left halo, floats, 16-B rounded
     constexpr int HR = (((KX - 1 - HX) * C + 3) / 4) * 4;      // right halo
-    constexpr int NF4 = 1 + HL / 4 + HR / 4;                   // float4s a thread reads per row
+    constexpr int NF4 = 1 + HL / 4 + HR / 4;                   // float4s a thread reads per row per column
     constexpr int OFF = HL - HX * C;                           // in[] index of tap 0 of output 0
     extern __shared__ __align__(128) float ss_smem[];
-    __shared__ __align__(8) uint64_t full_bar[SS_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[SS_STAGES];
-    __shared__ int row_valid[SS_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[G::MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[G::MAX_STAGES];
+    __shared__ int row_valid[G::MAX_STAGES];
+    const SepStreamParams& P = R.g;
     const uint32_t tid = threadIdx.x;
+    const uint32_t nst = R.stages;
     if (tid == 0) {
-        for (int s = 0; s < SS_STAGES; ++s) { ss_mbar_init(&full_bar[s], 1); ss_mbar_init(&empty_bar[s], SS_COLS4 / 32); }
+        for (uint32_t s = 0; s < nst; ++s) { ss_mbar_init(&full_bar[s], 1); ss_mbar_init(&empty_bar[s], G::COLS4 / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const size_t img_floats = (size_t)P.rowlen * P.rows;
-    uint32_t k = 0;  // running staged-row counter: stage = k % STAGES, use = k / STAGES
+    uint32_t stage = 0, phase = 0;
 
-    if (tid >= SS_COLS4) {
-        if (tid != SS_COLS4) return;
+    if (tid >= G::COLS4) {
+        if (tid != G::COLS4) return;
         // ── producer lane ──
+        bool first_lap = true;
         for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
             const uint32_t strip = u % P.strips, rest = u / P.strips;
             const uint32_t chunk = rest % P.chunks, img = rest / P.chunks;
-            const int e0 = (int)(strip * SS_EW);
-            const int g0 = max(e0 - HL, 0), g1 = min(e0 + SS_EW + HR, (int)P.rowlen);  // floats, multiples of 4
+            const int e0 = (int)(strip * G::EW);
+            const int g0 = max(e0 - HL, 0), g1 = min(e0 + G::EW + HR, (int)P.rowlen);  // floats, multiples of 4
             const uint32_t bytes = (uint32_t)(g1 - g0) * 4u;
             const uint32_t slot_off = (uint32_t)(g0 - (e0 - HL));                        // floats into the slot
             const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
             const float* base = src + (size_t)img * img_floats + g0;
-            for (int iy = y_first - HY; iy < y_end + (KY - 1 - HY); ++iy, ++k) {
-                const uint32_t stage = k % SS_STAGES, use = k / SS_STAGES;
-                if (use > 0) ss_mbar_wait(&empty_bar[stage], (use - 1u) & 1u);
+            for (int iy = y_first - HY; iy < y_end + (KY - 1 - HY); ++iy) {
+                if (!first_lap) ss_mbar_wait(&empty_bar[stage], phase ^ 1u);
                 const bool valid = iy >= 0 && iy < (int)P.rows;
                 row_valid[stage] = valid ? 1 : 0;
                 if (valid) {
@@ -258,119 +319,175 @@ __global__ void __launch_bounds__(SS_THREADS) sep_filter_stream_kernel(const flo
                 } else {
                     ss_mbar_arrive(&full_bar[stage]);
                 }
+                if (++stage == nst) { stage = 0; phase ^= 1u; first_lap = false; }
             }
         }
         return;
     }
 
-    // ── consumers: one float4 column each ──
+    // ── consumers: NV float4 columns each ──
+    PairConst pc;
+    pc.nz = ss_pack(R.neg_zero, R.neg_zero); pc.one = ss_pack(R.one, R.one); pc.zero = ss_pack(0.0f, 0.0f);
+    ss_u64 kyp[SOBEL ? 1 : KY];
+    if constexpr (!SOBEL) {
+#pragma unroll
+        for (int t = 0; t < KY; ++t) kyp[t] = ss_pack(taps.ky[t], taps.ky[t]);
+    }
     const bool lane0 = (tid & 31u) == 0;
-    for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
-        const uint32_t strip = u % P.strips, rest = u / P.strips;
-        const uint32_t chunk = rest % P.chunks, img = rest / P.chunks;
-        const int e0 = (int)(strip * SS_EW);
-        const int e = e0 + 4 * (int)tid;                 // first global float of this thread's outputs
-        const bool active = e < (int)P.rowlen;
-        const bool edge_unit = (e0 - HL < 0) || (e0 + SS_EW + HR > (int)P.rowlen);
-        const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
-        float* out = dst + (size_t)img * img_floats + (size_t)y_first * P.rowlen + e;
-        float winA[KY][4], winB[SOBEL ? KY : 1][4];
+
+    // one unit (strip x row chunk) for this thread; EDGE = the strip touches the left or right image border (float4s
+    // outside the row are zeroed in registers), interior strips carry no bounds logic at all
+    auto consume = [&](auto edge_tag, int e0, int y_first, int y_end, float* __restrict__ out) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        const int e = e0 + 4 * (int)tid;                 // first global float of this thread's column 0
+        bool act[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) act[v] = !EDGE || (e + v * (G::COLS4 * 4) < (int)P.rowlen);
+        ss_u64 winA[KY][NV][2], winB[SOBEL ? KY : 1][NV][2];
 #pragma unroll
         for (int t = 0; t < KY; ++t)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { winA[t][j] = 0.0f; if (SOBEL) winB[t][j] = 0.0f; }
+            for (int v = 0; v < NV; ++v) { winA[t][v][0] = winA[t][v][1] = pc.zero; if (SOBEL) winB[t][v][0] = winB[t][v][1] = pc.zero; }
         int iy = y_first - HY;
         const int iy_end = y_end + (KY - 1 - HY);
         while (iy < iy_end) {
 #pragma unroll
             for (int s = 0; s < KY; ++s) {   // unrolled: window slot indices are compile-time
                 if (iy >= iy_end) break;
-                const uint32_t stage = k % SS_STAGES, use = k / SS_STAGES;
-                ss_mbar_wait(&full_bar[stage], use & 1u);
-                float hA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, hB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (row_valid[stage] && active) {
-                    const float4* sp = reinterpret_cast<const float4*>(ss_smem + (size_t)stage * P.slot_floats) + tid;
-                    float in[NF4 * 4];
+                ss_mbar_wait(&full_bar[stage], phase);
+                const bool valid = row_valid[stage] != 0;
+                const float4* sp = reinterpret_cast<const float4*>(ss_smem + (size_t)stage * P.slot_floats) + tid;
 #pragma unroll
-                    for (int q = 0; q < NF4; ++q) {
-                        float4 v = sp[q];
-                        if (edge_unit) {
-                            const int gi = e - HL + 4 * q;   // global float index of this float4
-                            if (gi < 0 || gi >= (int)P.rowlen) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                for (int v = 0; v < NV; ++v) {
+                    float hA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, hB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (valid && act[v]) {
+                        float in[NF4 * 4];
+#pragma unroll
+                        for (int q = 0; q < NF4; ++q) {
+                            float4 x = sp[v * G::COLS4 + q];
+                            if (EDGE) {
+                                const int gi = e + v * (G::COLS4 * 4) - HL + 4 * q;   // global float index of this float4
+                                if (gi < 0 || gi >= (int)P.rowlen) x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                            }
+                            in[4 * q] = x.x; in[4 * q + 1] = x.y; in[4 * q + 2] = x.z; in[4 * q + 3] = x.w;
                         }
-                        in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
-                    }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if constexpr (SOBEL) {
-                            auto get = [&](int t) { return in[OFF + j + t * C]; };
-                            hA[j] = SobelAcc<KX, true, 0>::run(0.0f, get);    // derivative taps along x  (gx)
-                            hB[j] = SobelAcc<KX, false, 0>::run(0.0f, get);   // smoothing taps along x   (gy)
-                        } else {
-                            float a = 0.0f;
+                        for (int j = 0; j < 4; ++j) {
+                            if constexpr (SOBEL) {
+                                auto get = [&](int t) { return in[OFF + j + t * C]; };
+                                hA[j] = SobelAcc<KX, true, 0>::run(0.0f, get);    // derivative taps along x  (gx)
+                                hB[j] = SobelAcc<KX, false, 0>::run(0.0f, get);   // smoothing taps along x   (gy)
+                            } else {
+                                float a = fmaf(in[OFF + j], taps.kx[0], 0.0f);   // == 0 + in*k
 #pragma unroll
-                            for (int t = 0; t < KX; ++t) a += in[OFF + j + t * C] * taps.kx[t];
-                            hA[j] = a;
+                                for (int t = 1; t < KX; ++t) a += in[OFF + j + t * C] * taps.kx[t];
+                                hA[j] = a;
+                            }
                         }
                     }
+                    winA[s][v][0] = ss_pack(hA[0], hA[1]); winA[s][v][1] = ss_pack(hA[2], hA[3]);
+                    if (SOBEL) { winB[s][v][0] = ss_pack(hB[0], hB[1]); winB[s][v][1] = ss_pack(hB[2], hB[3]); }
                 }
                 __syncwarp();
                 if (lane0) ss_mbar_arrive(&empty_bar[stage]);
-                ++k;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { winA[s][j] = hA[j]; if (SOBEL) winB[s][j] = hB[j]; }
+                if (++stage == nst) { stage = 0; phase ^= 1u; }
                 // the row that just became complete: r = iy - (KY-1-HY); its window is slots s+1 … s+KY (mod KY), oldest first
-                const int r = iy - (KY - 1 - HY);
-                if (r >= y_first && active) {
-                    float o[4];
+                if (iy - (KY - 1 - HY) >= y_first) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if constexpr (SOBEL) {
-                            auto getA = [&](int t) { return winA[(s + 1 + t) % KY][j]; };
-                            auto getB = [&](int t) { return winB[(s + 1 + t) % KY][j]; };
-                            const float gx = SobelAcc<KY, false, 0>::run(0.0f, getA);  // smoothing along y
-                            const float gy = SobelAcc<KY, true, 0>::run(0.0f, getB);   // derivative along y
-                            o[j] = sqrtf(gx * gx + gy * gy);
-                        } else {
-                            float acc = 0.0f;
+                    for (int v = 0; v < NV; ++v) {
+                        if (!act[v]) continue;
+                        float o[4];
 #pragma unroll
-                            for (int t = 0; t < KY; ++t) acc += winA[(s + 1 + t) % KY][j] * taps.ky[t];
-                            o[j] = acc;
+                        for (int h = 0; h < 2; ++h) {
+                            if constexpr (SOBEL) {
+                                auto getA = [&](int t) { return winA[(s + 1 + t) % KY][v][h]; };
+                                auto getB = [&](int t) { return winB[(s + 1 + t) % KY][v][h]; };
+                                const ss_u64 gx = SobelAccPair<KY, false, 0>::run(pc.zero, pc, getA);  // smoothing along y
+                                const ss_u64 gy = SobelAccPair<KY, true, 0>::run(pc.zero, pc, getB);   // derivative along y
+                                const ss_u64 m = pair_add(pair_mul(gx, gx, pc), pair_mul(gy, gy, pc), pc);   // gx*gx + gy*gy, unfused
+                                float m0, m1;
+                                ss_unpack(m, m0, m1);
+                                o[2 * h] = sqrtf(m0); o[2 * h + 1] = sqrtf(m1);
+                            } else {
+                                ss_u64 acc = ss_fma2(winA[(s + 1) % KY][v][h], kyp[0], pc.zero);   // == 0 + w*k
+#pragma unroll
+                                for (int t = 1; t < KY; ++t) acc = pair_add(acc, pair_mul(winA[(s + 1 + t) % KY][v][h], kyp[t], pc), pc);
+                                ss_unpack(acc, o[2 * h], o[2 * h + 1]);
+                            }
                         }
+                        stg_stream_f4(reinterpret_cast<float4*>(out + v * (G::COLS4 * 4)), make_float4(o[0], o[1], o[2], o[3]));
                     }
-                    stg_stream_f4(reinterpret_cast<float4*>(out + (size_t)(r - y_first) * P.rowlen), make_float4(o[0], o[1], o[2], o[3]));
+                    out += P.rowlen;
                 }
                 ++iy;
             }
-            // a partial pass through the unrolled body leaves the window rotated: only happens at the end of a unit,
-            // after which the window is re-zeroed — nothing to fix up.
         }
+    };
+
+    for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
+        const uint32_t strip = u % P.strips, rest = u / P.strips;
+        const uint32_t chunk = rest % P.chunks, img = rest / P.chunks;
+        const int e0 = (int)(strip * G::EW);
+        const bool edge_unit = (e0 - HL < 0) || (e0 + G::EW + HR > (int)P.rowlen);
+        const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
+        float* out = dst + (size_t)img * img_floats + (size_t)y_first * P.rowlen + e0 + 4 * (int)tid;
+        if (edge_unit) consume(std::true_type{}, e0, y_first, y_end, out);
+        else consume(std::false_type{}, e0, y_first, y_end, out);
     }
 }
 
-template <int C, int KX, int KY, bool SOBEL>
-static int launch_sep_stream(cudaStream_t s, const float* src, float* dst, const SepTaps& taps, uint32_t cols, uint32_t rows,
-                             uint32_t batch) {
+static int ss_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int C, int KX, int KY, bool SOBEL, int NV>
+static int launch_sep_stream2(cudaStream_t s, const float* src, float* dst, const SepTaps& taps, uint32_t cols, uint32_t rows,
+                              uint32_t batch) {
+    using G = SS2<NV>;
     constexpr int HX = KX / 2;
     constexpr int HL = ((HX * C + 3) / 4) * 4, HR = (((KX - 1 - HX) * C + 3) / 4) * 4;
-    SepStreamParams P;
+    static const int tune_stages = ss_env_int("KB200_SS_STAGES", 0), tune_ctas = ss_env_int("KB200_SS_CTAS", 0);
+    SepStream2Params R;
+    SepStreamParams& P = R.g;
     P.rowlen = cols * C; P.rows = rows; P.batch = batch;
-    P.strips = (P.rowlen + SS_EW - 1) / SS_EW;
-    P.slot_floats = SS_EW + HL + HR;
-    const size_t smem = (size_t)P.slot_floats * 4 * SS_STAGES;
-    const size_t ctas = (size_t)device_info().sm_count * 6;
-    // chunk height: ~12 units per CTA, at least 32 rows so the K-1 halo rows stay a few percent
+    P.strips = (P.rowlen + G::EW - 1) / G::EW;
+    P.slot_floats = G::EW + HL + HR;
+    // B200 sweep (profiles/r1_filters.md): blur is best at 6 CTAs x 4 stages, sobel (fewer bytes per instruction) at 7 x 3
+    const uint32_t stages = (tune_stages >= 2 && tune_stages <= G::MAX_STAGES) ? (uint32_t)tune_stages : (SOBEL ? 3u : 4u);
+    const int per_sm = tune_ctas > 0 ? tune_ctas : (SOBEL ? 7 : 6);
+    const size_t smem = (size_t)P.slot_floats * 4 * stages;
+    auto kern = sep_filter_stream2_kernel<C, KX, KY, SOBEL, NV>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
+    }
+    // persistent CTAs must all be co-resident: never ask for more per SM than the occupancy calculator grants
+    int resident = 0;
+    {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, G::THREADS, smem);
+        if (e != cudaSuccess || resident < 1) return fail(KB200_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+    }
+    static const bool debug = ss_env_int("KB200_SS_DEBUG", 0) != 0;
+    if (debug) fprintf(stderr, "[kb200] sep_stream2 C=%d K=%d sobel=%d NV=%d: stages=%u smem=%zu per_sm=%d resident=%d\n", C, KX, (int)SOBEL, NV, stages, smem, per_sm, resident);
+    const size_t ctas = (size_t)device_info().sm_count * std::min(per_sm, resident);
+    // chunk height: ~12 units per CTA keeps the persistent grid balanced (a search that traded balance against the
+    // KY-1 halo rows per chunk measured 8-13 % slower on B200: long chunks leave the ragged last strip's CTAs idle);
+    // at least 32 rows so the halo re-reads stay near 10 %
+    static const int tune_rc = ss_env_int("KB200_SS_RC", 0);
     const size_t total = (size_t)P.strips * batch * rows;
-    uint32_t rc = (uint32_t)std::max<size_t>(32, total / (ctas * 12));
+    uint32_t rc = tune_rc > 0 ? (uint32_t)tune_rc : (uint32_t)std::max<size_t>(32, total / (ctas * 12));
     rc = std::min(rc, rows);
     P.rows_per_chunk = rc;
     P.chunks = (rows + rc - 1) / rc;
     const size_t nunits = (size_t)P.strips * P.chunks * batch;
     if (nunits > 0x7FFFFFFFull) return fail(KB200_ERR_DIMS_TOO_LARGE, "too many filter work units (%zu)", nunits);
     P.nunits = (uint32_t)nunits;
+    R.stages = stages;
+    R.neg_zero = -0.0f; R.one = 1.0f;
     const unsigned grid = (unsigned)std::min<size_t>(nunits, ctas);
-    sep_filter_stream_kernel<C, KX, KY, SOBEL><<<grid, SS_THREADS, smem, s>>>(src, dst, taps, P);
-    return check_launch("sep_filter_stream_kernel");
+    kern<<<grid, G::THREADS, smem, s>>>(src, dst, taps, R);
+    return check_launch("sep_filter_stream2_kernel");
 }
 
 // returns true if a streaming instance exists for (C, kx, ky, sobel) and launched it (status in *st)
@@ -380,7 +497,7 @@ static bool try_sep_stream(cudaStream_t s, const float* src, float* dst, const S
     const int kx = taps.kxn, ky = taps.kyn;
 #define KB200_SS_CASE(CC, KK, SB)                                                             \
     if (C == CC && kx == KK && ky == KK && sobel == SB) {                                     \
-        *st = launch_sep_stream<CC, KK, KK, SB>(s, src, dst, taps, cols, rows, batch);        \
+        *st = launch_sep_stream2<CC, KK, KK, SB, 1>(s, src, dst, taps, cols, rows, batch);    \
         return true;                                                                          \
     }
     KB200_SS_CASE(3, 5, false) KB200_SS_CASE(3, 3, false) KB200_SS_CASE(3, 7, false)

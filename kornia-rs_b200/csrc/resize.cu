@@ -130,7 +130,9 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* 
     bilinear_tap_q14(y, scale_y, sh, &yi, &fy);
     const unsigned long long fx1 = 16384u - fx, fy1 = 16384u - fy;
     const uint8_t* r0 = s + ((size_t)yi * sw + xi) * C;
-    const uint8_t* r1 = r0 + (size_t)sw * C;
+    // fy == 0 (e.g. every row of an odd integer downscale): `bot * 0` contributes exactly nothing in the Q28
+    // integer sum, so the y1 row is not addressed at all — one source row in three is read at 2160 -> 720
+    const uint8_t* r1 = fy ? r0 + (size_t)sw * C : r0;
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) {
         const unsigned long long p00 = r0[ch], p01 = r0[C + ch], p10 = r1[ch], p11 = r1[C + ch];

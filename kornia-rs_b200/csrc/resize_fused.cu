@@ -8,6 +8,8 @@
 // columns ≥ fma_bulk use the scalar (mul, add) leaf — so the output is bit-identical to what the
 // reference produces on the chosen CPU (x86 AVX2+FMA: bulk = dst_w & ~7, or & ~15 on the 2x path).
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 #include "kb200_common.cuh"
 #include "resize_fused.cuh"
@@ -68,8 +70,7 @@ __global__ void __launch_bounds__(256) fused_resize_gather_kernel(const uint8_t*
     }
 }
 
-int launch_fused_resize_staged(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch,
-                               bool* handled);
+int launch_fused_resize_rows(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch, bool* handled);
 
 FusedParams make_fused_params(uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, const float scale[3], const float bias[3], int leaf) {
     FusedParams p;
@@ -112,7 +113,7 @@ int launch_fused_resize(cudaStream_t s, const uint8_t* src, float* dst, const Fu
     const bool box2x = (p.sw == 2 * p.dw && p.sh == 2 * p.dh);
     if (!box2x) {
         bool handled = false;
-        KB200_TRY(launch_fused_resize_staged(s, src, dst, p, batch, &handled));
+        KB200_TRY(launch_fused_resize_rows(s, src, dst, p, batch, &handled));
         if (handled) return KB200_OK;
     }
     dim3 block(32, 8), grid(div_up(p.dw, 32), div_up(p.dh, 8), batch);
@@ -185,33 +186,31 @@ KB200_API void kb200_resize_row_plan(uint32_t src_h, uint32_t dst_h, uint32_t* p
 // ─────────────────────────────────────────────────────────────────────────────────────────────
 // Row-span staged kernel (the config-2 fast path).
 //
-// ncu history (profiles/r1_cfg2_*.md): the gather kernel above executes 170 warp-instructions per
-// output pixel at 79 % issue-slot utilisation with DRAM at 60 % — instruction-bound, not memory-bound.
-// This kernel moves the source reads off the LSU, cuts the instruction count and keeps a deep queue of
-// TMA copies in flight:
+// ncu history (profiles/r1_cfg2_fused_resize.md): the gather kernel above executes 170 warp-instructions per output
+// pixel at 79 % issue-slot utilisation with DRAM at 60 % — instruction-bound.  A first staged kernel (TMA row spans,
+// one destination column per thread) reached 100 instructions/pixel and 0.71-0.90 of the roofline but was still
+// issue-bound: ~45 of those instructions were per-ROW bookkeeping repeated for a single pixel.  The kernel below keeps
+// the staging scheme and spreads that bookkeeping over several pixels per thread (35 instructions/pixel in point
+// mode; issue utilisation 35 %; DRAM-bound at ~90 % of the measured copy bandwidth):
 //
 //   * work unit = (image, column tile of TW destination columns, chunk of RC destination rows); CTAs are
 //     persistent and walk their units with carry arithmetic (no integer division in the loop).
-//   * per destination row, the two source rows it taps are copied — only the byte span
-//     [x0(first col), x1(last col)] the column tile touches, rounded out to 16 B — global -> shared by
-//     the TMA engine (cp.async.bulk 1-D, SASS UBLKCP), completion counted on an mbarrier (expect_tx).
-//     Source rows no destination row taps (1 of every 3 at scale 3) are never addressed.
-//   * STAGES-deep ring, one destination row per stage, running continuously across units.  Warp 8 is the
-//     producer (one elected lane: wait `empty`, publish the row's y-weight, issue the 2 copies); warps
-//     0-7 are consumers (wait `full`, compute one row, arrive on `empty`).  No __syncthreads in the loop.
-//   * a consumer thread owns ONE destination column for the whole unit: the x-side of the sampler
-//     (fx, x0, wx, smem byte offset, funnel shift) is computed once per unit and lives in registers.
-//   * taps are read as three aligned 32-bit words per source row and funnel-shifted into place; a byte
-//     becomes a float with one PRMT into the mantissa of 2^23; `b - a` is formed on the biased values
-//     (exact) and only the base taps are unbiased (one FADD).
+//   * per destination row, the source rows it taps are copied — only the byte span [x0(first col), x1(last col)]
+//     the column tile touches, rounded out to 16 B — global -> shared by the TMA engine (cp.async.bulk 1-D, SASS
+//     UBLKCP), completion counted on an mbarrier (expect_tx).  Source rows with no (or a zero) weight are never
+//     addressed: 2 of every 3 at scale 3.
+//   * a short ring (3 stages), one destination row per stage, running continuously across units.  Warp 4 is the
+//     producer (one elected lane: wait `empty`, publish the row's y-weight, issue the copies); warps 0-3 are
+//     consumers (wait `full`, compute one row, arrive on `empty`).  No __syncthreads in the loop.
+//   * the x-side of the sampler (fx, x0, wx, smem byte offset, funnel shift) is computed once per unit per column
+//     and lives in registers.
+//   * taps are read as three aligned 32-bit words per source row and funnel-shifted into place; a byte becomes a
+//     float with one PRMT into the mantissa of 2^23; `b - a` is formed on the biased values (exact) and only the
+//     base taps are unbiased (one FADD).
 //   * stores: a warp writes 32 consecutive floats of one channel plane = one full 128-B line.
 //
 // Arithmetic is identical to the gather kernel (and therefore to the reference leaf selected).
 namespace kb200 {
-
-static constexpr int FS_TW = 256;              // destination columns per unit = consumer threads per CTA
-static constexpr int FS_STAGES = 8;            // ring depth (destination rows in flight per CTA)
-static constexpr int FS_THREADS = FS_TW + 32;  // + producer warp
 
 struct FusedStagedParams {
     FusedParams p;
@@ -278,83 +277,97 @@ struct UnitWalk {
     }
 };
 
-// One destination row for one destination column out of a staged pair of source-row spans.
-// SINGLE: the row's vertical weight is exactly 0 (odd integer downscale, e.g. 2160 -> 720), so the y1 row was never
-// staged.  val = top + 0*(bot - top) == top bit-for-bit for the finite, non-negative `top` bytes produce (a -0 product
-// added to +0 gives +0), and fmaf(bot - top, 0, top) == top likewise — the tap is dropped, not approximated.
-template <bool FUSED_LEAF, bool EDGE, bool SINGLE>
-__device__ __forceinline__ void fs_row(const uint8_t* __restrict__ rp, uint32_t slot_bytes, uint32_t shft, float wx, float wy,
-                                       float s0, float s1, float s2, float o0, float o1, float o2, float& q0, float& q1, float& q2) {
-    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(rp);
-    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(rp + slot_bytes);
-    const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
-    uint32_t lo0 = __funnelshift_r(a0, a1, shft), hi0 = __funnelshift_r(a1, a2, shft);  // bytes off..off+3 | off+4..off+7
-    uint32_t lo1 = 0, hi1 = 0;
-    if (!SINGLE) {
-        const uint32_t c0 = r1[0], c1 = r1[1], c2 = r1[2];
-        lo1 = __funnelshift_r(c0, c1, shft); hi1 = __funnelshift_r(c1, c2, shft);
-    }
-    if (EDGE) {  // right image edge: the +1 tap replicates x0 — bytes 3..5 := bytes 0..2
-        hi0 = __byte_perm(lo0, 0, 0x4421); lo0 = __byte_perm(lo0, 0, 0x0210);
-        hi1 = __byte_perm(lo1, 0, 0x4421); lo1 = __byte_perm(lo1, 0, 0x0210);
-    }
-    float res[3];
+// Several destination columns per thread + per-launch specialisation.
+//
+// A consumer thread owns NPX columns (t, t+128, ..., all lane-contiguous), so the per-row bookkeeping (mbarrier
+// wait/arrive, ring index, pointer bumps) is paid once per NPX pixels, and the sampler is specialised per LAUNCH on
+// what the geometry makes exactly zero:
+//
+//   FR_GENERAL  two source rows per destination row (the y1 row is skipped by the producer when its weight is 0;
+//               the consumer then multiplies stale-but-finite bytes by 0, which is exact).
+//   FR_YZERO    every destination row has wy == 0 (odd integer vertical ratio, or 1:1): one source row per stage.
+//   FR_POINT    additionally every column has wx == 0: out = byte * scale + bias — three byte loads per pixel.
+//
+// A right-edge column (x1 == x0) is folded into the general arithmetic by forcing wx = 0: b == a there, so
+// a + wx*(b-a) == a for any wx, and with wx = 0 the (finite) neighbour byte that is read instead contributes ±0.
+static constexpr int FR_CT = 128;               // consumer threads per CTA
+static constexpr int FR_THREADS = FR_CT + 32;   // + producer warp
+static constexpr int FR_MAX_STAGES = 16;
+enum { FR_GENERAL = 0, FR_YZERO = 1, FR_POINT = 2 };
+
+struct FusedRowsParams {
+    FusedStagedParams g;   // geometry + unit walk (tiles_x counts tiles of FR_CT*NPX columns)
+    uint32_t stages;       // ring depth
+    uint32_t stage_bytes;  // slot_bytes * (rows staged per destination row)
+};
+
+template <int MODE>
+__device__ __forceinline__ void fr_pixel(const uint8_t* __restrict__ rp, uint32_t slot_bytes, uint32_t shft, float wx, float wy, bool fma_leaf,
+                                         float s0, float s1, float s2, float o0, float o1, float o2, float& q0, float& q1, float& q2) {
+    float v[3];
+    if (MODE == FR_POINT) {
+        v[0] = (float)rp[0]; v[1] = (float)rp[1]; v[2] = (float)rp[2];
+    } else {
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(rp);
+        const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2];
+        const uint32_t lo0 = __funnelshift_r(a0, a1, shft), hi0 = __funnelshift_r(a1, a2, shft);  // bytes off..off+3 | off+4..off+7
+        uint32_t lo1 = 0, hi1 = 0;
+        if (MODE == FR_GENERAL) {
+            const uint32_t* r1 = reinterpret_cast<const uint32_t*>(rp + slot_bytes);
+            const uint32_t c0 = r1[0], c1 = r1[1], c2 = r1[2];
+            lo1 = __funnelshift_r(c0, c1, shft); hi1 = __funnelshift_r(c1, c2, shft);
+        }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        // biased floats 2^23 + byte: a = tap(x0,y0), b = tap(x1,y0), c = tap(x0,y1), d = tap(x1,y1)
-        const float ab = __uint_as_float(__byte_perm(lo0, 0x4B000000u, 0x7650u + (uint32_t)c));
-        const float bb = __uint_as_float(c == 0 ? __byte_perm(lo0, 0x4B000000u, 0x7653u) : __byte_perm(hi0, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
-        const float a = ab - 8388608.0f;  // exact
-        const float dba = bb - ab;        // exact: (2^23+b) - (2^23+a) = b - a
-        const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), bi = c == 0 ? o0 : (c == 1 ? o1 : o2);
-        if (SINGLE) {
-            res[c] = FUSED_LEAF ? fmaf(fmaf(dba, wx, a), sc, bi) : (a + wx * dba) * sc + bi;
-            continue;
-        }
-        const float cb = __uint_as_float(__byte_perm(lo1, 0x4B000000u, 0x7650u + (uint32_t)c));
-        const float db = __uint_as_float(c == 0 ? __byte_perm(lo1, 0x4B000000u, 0x7653u) : __byte_perm(hi1, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
-        const float cc = cb - 8388608.0f, ddc = db - cb;
-        if (FUSED_LEAF) {  // resize/fused.rs:475-478
-            const float top = fmaf(dba, wx, a);
-            const float bot = fmaf(ddc, wx, cc);
-            res[c] = fmaf(fmaf(bot - top, wy, top), sc, bi);
-        } else {           // resize/fused.rs:286-317
-            const float top = a + wx * dba;
-            const float bot = cc + wx * ddc;
-            const float val = top + wy * (bot - top);
-            res[c] = val * sc + bi;
+        for (int c = 0; c < 3; ++c) {
+            // biased floats 2^23 + byte: a = tap(x0,y0), b = tap(x1,y0), c = tap(x0,y1), d = tap(x1,y1)
+            const float ab = __uint_as_float(__byte_perm(lo0, 0x4B000000u, 0x7650u + (uint32_t)c));
+            const float bb = __uint_as_float(c == 0 ? __byte_perm(lo0, 0x4B000000u, 0x7653u) : __byte_perm(hi0, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
+            const float a = ab - 8388608.0f;  // exact
+            const float dba = bb - ab;        // exact: (2^23+b) - (2^23+a) = b - a
+            const float top = fma_leaf ? fmaf(dba, wx, a) : a + wx * dba;   // resize/fused.rs:475 | :286
+            if (MODE == FR_YZERO) { v[c] = top; continue; }
+            const float cb = __uint_as_float(__byte_perm(lo1, 0x4B000000u, 0x7650u + (uint32_t)c));
+            const float db = __uint_as_float(c == 0 ? __byte_perm(lo1, 0x4B000000u, 0x7653u) : __byte_perm(hi1, 0x4B000000u, 0x7650u + (uint32_t)(c - 1)));
+            const float cc = cb - 8388608.0f, ddc = db - cb;
+            const float bot = fma_leaf ? fmaf(ddc, wx, cc) : cc + wx * ddc;
+            v[c] = fma_leaf ? fmaf(bot - top, wy, top) : top + wy * (bot - top);
         }
     }
-    q0 = res[0]; q1 = res[1]; q2 = res[2];
+    if (fma_leaf) { q0 = fmaf(v[0], s0, o0); q1 = fmaf(v[1], s1, o1); q2 = fmaf(v[2], s2, o2); }   // resize/fused.rs:478
+    else          { q0 = v[0] * s0 + o0;     q1 = v[1] * s1 + o1;     q2 = v[2] * s2 + o2; }       // :317
 }
 
-__global__ void __launch_bounds__(FS_THREADS) fused_resize_staged_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
-                                                                         const __grid_constant__ FusedStagedParams P) {
+template <int NPX, int MODE, bool ALLFMA>
+__global__ void __launch_bounds__(FR_THREADS) fused_rows_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst,
+                                                                const __grid_constant__ FusedRowsParams R) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[FS_STAGES];
-    __shared__ __align__(8) uint64_t empty_bar[FS_STAGES];
-    __shared__ float wy_s[FS_STAGES];
+    __shared__ __align__(8) uint64_t full_bar[FR_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[FR_MAX_STAGES];
+    __shared__ float wy_s[FR_MAX_STAGES];
+    constexpr uint32_t TW = FR_CT * NPX;
+    const FusedStagedParams& P = R.g;
     const FusedParams& p = P.p;
     const uint32_t tid = threadIdx.x;
-    const uint32_t stage_bytes = P.slot_bytes * 2u;
+    const uint32_t nst = R.stages;
     const size_t frame_bytes = (size_t)P.row_bytes * p.src_rows;
     const size_t plane = (size_t)p.dw * p.dh;
 
     if (tid == 0) {
-        for (int s = 0; s < FS_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], FS_TW / 32); }
+        for (uint32_t s = 0; s < nst; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], FR_CT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     UnitWalk w;
     w.init(blockIdx.x, P);
-    uint32_t k = 0;  // running row counter of this CTA: stage = k % STAGES, use = k / STAGES
+    uint32_t stage = 0, phase = 0;  // ring position, running continuously across units
 
-    if (tid >= FS_TW) {
+    if (tid >= FR_CT) {
         // ── producer warp: one elected lane ──
-        if (tid != FS_TW) return;
+        if (tid != FR_CT) return;
+        bool first_lap = true;
         for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x, w.advance(P)) {
-            const uint32_t dx0 = w.tx * FS_TW, dx1 = min(dx0 + FS_TW, p.dw) - 1u;
+            const uint32_t dx0 = w.tx * TW, dx1 = min(dx0 + TW, p.dw) - 1u;
             uint32_t xa, xb, tmp;
             float wtmp;
             fused_axis(dx0, p.scale_x, p.sw, &xa, &tmp, &wtmp);
@@ -364,18 +377,18 @@ __global__ void __launch_bounds__(FS_THREADS) fused_resize_staged_kernel(const u
             const uint32_t bytes = b1 - b0;
             const uint8_t* frame = src + (size_t)w.img * frame_bytes + b0;
             const uint32_t y_first = w.cy * P.rows_per_chunk, y_end = min(y_first + P.rows_per_chunk, p.dh);
-            for (uint32_t dy = y_first; dy < y_end; ++dy, ++k) {
-                const uint32_t stage = k % FS_STAGES, use = k / FS_STAGES;
-                if (use > 0) mbar_wait(&empty_bar[stage], (use - 1u) & 1u);  // consumers drained the previous tenant
+            for (uint32_t dy = y_first; dy < y_end; ++dy) {
+                if (!first_lap) mbar_wait(&empty_bar[stage], phase ^ 1u);  // consumers drained the previous tenant
                 uint32_t y0, y1;
                 float wy;
                 fused_axis(dy, p.scale_y, p.sh, &y0, &y1, &wy);
-                wy_s[stage] = wy;  // before the arrive(release): covered by the consumers' acquire on `full`
-                uint8_t* sbase = smem_raw + (size_t)stage * stage_bytes;
-                const bool single = (wy == 0.0f);  // zero vertical weight: the y1 row contributes exactly nothing
-                mbar_expect_tx(&full_bar[stage], single ? bytes : bytes * 2u);
+                uint8_t* sbase = smem_raw + (size_t)stage * R.stage_bytes;
+                const bool two = (MODE == FR_GENERAL) && (wy != 0.0f);  // a zero-weight y1 row is never fetched
+                if (MODE == FR_GENERAL) wy_s[stage] = wy;  // before the arrive(release): covered by the consumers' acquire on `full`
+                mbar_expect_tx(&full_bar[stage], two ? bytes * 2u : bytes);
                 tma_load_1d(sbase, frame + (size_t)fused_row_slot(p, y0) * P.row_bytes, bytes, &full_bar[stage]);
-                if (!single) tma_load_1d(sbase + P.slot_bytes, frame + (size_t)fused_row_slot(p, y1) * P.row_bytes, bytes, &full_bar[stage]);
+                if (two) tma_load_1d(sbase + P.slot_bytes, frame + (size_t)fused_row_slot(p, y1) * P.row_bytes, bytes, &full_bar[stage]);
+                if (++stage == nst) { stage = 0; phase ^= 1u; first_lap = false; }
             }
         }
         return;
@@ -386,71 +399,136 @@ __global__ void __launch_bounds__(FS_THREADS) fused_resize_staged_kernel(const u
     const float o0 = p.bias[0], o1 = p.bias[1], o2 = p.bias[2];
     const bool lane0 = (tid & 31u) == 0;
     for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x, w.advance(P)) {
-        const uint32_t dx0 = w.tx * FS_TW;
-        const uint32_t x = dx0 + tid;
-        // x-side of the sampler, once per unit
-        uint32_t x0, x1, xa, tmp;
-        float wx, wtmp;
-        fused_axis(min(x, p.dw - 1u), p.scale_x, p.sw, &x0, &x1, &wx);
+        const uint32_t dx0 = w.tx * TW;
+        uint32_t xa, tmp;
+        float wtmp;
         fused_axis(dx0, p.scale_x, p.sw, &xa, &tmp, &wtmp);
-        const uint32_t off = x0 * 3u - ((xa * 3u) & ~15u);  // byte offset of tap (x0) inside the staged span
-        const uint32_t woff = off & ~3u, shft = (off & 3u) * 8u;
-        const bool edge = (x1 == x0);
-        const bool fusedp = x < p.fma_bulk;
-        const bool active = x < p.dw;
+        const uint32_t b0 = (xa * 3u) & ~15u;
+        // x-side of the sampler, once per unit, for this thread's NPX columns
+        uint32_t off[NPX], shft[NPX];
+        float wx[NPX];
+        uint32_t act = 0, fm = 0;
+#pragma unroll
+        for (int j = 0; j < NPX; ++j) {
+            const uint32_t x = dx0 + tid + (uint32_t)j * FR_CT;
+            uint32_t x0, x1;
+            fused_axis(min(x, p.dw - 1u), p.scale_x, p.sw, &x0, &x1, &wx[j]);
+            if (x1 == x0) wx[j] = 0.0f;                      // right edge: b == a, any weight gives a — use the exact one
+            const uint32_t ob = x0 * 3u - b0;                // byte offset of tap x0 inside the staged span
+            if (MODE == FR_POINT) { off[j] = ob; shft[j] = 0; }
+            else { off[j] = ob & ~3u; shft[j] = (ob & 3u) * 8u; }
+            act |= (x < p.dw ? 1u : 0u) << j;
+            fm |= (x < p.fma_bulk ? 1u : 0u) << j;
+        }
         const uint32_t y_first = w.cy * P.rows_per_chunk, y_end = min(y_first + P.rows_per_chunk, p.dh);
-        float* out0 = dst + (size_t)w.img * plane * 3 + (size_t)y_first * p.dw + x;
+        float* out0 = dst + (size_t)w.img * plane * 3 + (size_t)y_first * p.dw + dx0 + tid;
         float* out1 = out0 + plane;
         float* out2 = out1 + plane;
-        for (uint32_t dy = y_first; dy < y_end; ++dy, ++k) {
-            const uint32_t stage = k % FS_STAGES, use = k / FS_STAGES;
-            mbar_wait(&full_bar[stage], use & 1u);
-            if (active) {
-                const uint8_t* rp = smem_raw + (size_t)stage * stage_bytes + woff;
-                const float wy = wy_s[stage];
+        for (uint32_t dy = y_first; dy < y_end; ++dy) {
+            mbar_wait(&full_bar[stage], phase);
+            const uint8_t* sbase = smem_raw + (size_t)stage * R.stage_bytes;
+            const float wy = (MODE == FR_GENERAL) ? wy_s[stage] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < NPX; ++j) {
                 float q0, q1, q2;
-#define KB200_FS_ROW(F, E, S) fs_row<F, E, S>(rp, P.slot_bytes, shft, wx, wy, s0, s1, s2, o0, o1, o2, q0, q1, q2)
-                if (wy == 0.0f) {  // CTA-uniform: the producer staged y0 only
-                    if (!edge) { if (fusedp) KB200_FS_ROW(true, false, true); else KB200_FS_ROW(false, false, true); }
-                    else       { if (fusedp) KB200_FS_ROW(true, true, true);  else KB200_FS_ROW(false, true, true); }
-                } else {
-                    if (!edge) { if (fusedp) KB200_FS_ROW(true, false, false); else KB200_FS_ROW(false, false, false); }
-                    else       { if (fusedp) KB200_FS_ROW(true, true, false);  else KB200_FS_ROW(false, true, false); }
-                }
-#undef KB200_FS_ROW
-                *out0 = q0; *out1 = q1; *out2 = q2;
+                fr_pixel<MODE>(sbase + off[j], P.slot_bytes, shft[j], wx[j], wy, ALLFMA || ((fm >> j) & 1u), s0, s1, s2, o0, o1, o2, q0, q1, q2);
+                if ((act >> j) & 1u) { out0[j * FR_CT] = q0; out1[j * FR_CT] = q1; out2[j * FR_CT] = q2; }
             }
             out0 += p.dw; out1 += p.dw; out2 += p.dw;
             __syncwarp();
             if (lane0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
     }
 }
 
-int launch_fused_resize_staged(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch,
-                               bool* handled) {
+// Are all the sampler's weights along one axis exactly zero (with the right-edge rule above)?  Same f32 expression
+// as the device (mul, add; no contraction), evaluated on the host once per launch.
+static bool axis_weights_all_zero(uint32_t dst_len, uint32_t src_len, float scale) {
+    for (uint32_t d = 0; d < dst_len; ++d) {
+        const float f = std::max(((float)d + 0.5f) * scale - 0.5f, 0.0f);
+        const uint32_t a = std::min((uint32_t)f, src_len - 1u);
+        const uint32_t b = std::min(a + 1u, src_len - 1u);
+        if (b != a && f - (float)a != 0.0f) return false;
+    }
+    return true;
+}
+
+template <int NPX, int MODE>
+static cudaError_t fr_launch(bool allfma, unsigned grid, size_t smem, cudaStream_t s, const uint8_t* src, float* dst, const FusedRowsParams& R) {
+    auto go = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, FR_THREADS, smem, s>>>(src, dst, R);
+        return cudaSuccess;
+    };
+    return allfma ? go(fused_rows_kernel<NPX, MODE, true>) : go(fused_rows_kernel<NPX, MODE, false>);
+}
+
+template <int MODE>
+static cudaError_t fr_launch_npx(int npx, bool allfma, unsigned grid, size_t smem, cudaStream_t s, const uint8_t* src, float* dst, const FusedRowsParams& R) {
+    switch (npx) {
+        case 1: return fr_launch<1, MODE>(allfma, grid, smem, s, src, dst, R);
+        case 2: return fr_launch<2, MODE>(allfma, grid, smem, s, src, dst, R);
+        case 3: return fr_launch<3, MODE>(allfma, grid, smem, s, src, dst, R);
+        case 4: return fr_launch<4, MODE>(allfma, grid, smem, s, src, dst, R);
+        default: return fr_launch<5, MODE>(allfma, grid, smem, s, src, dst, R);
+    }
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int launch_fused_resize_rows(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch, bool* handled) {
     *handled = false;
     const uint32_t row_bytes = p.sw * 3u;
     // TMA 1-D bulk copies need 16-B aligned rows; very strong downscales have sparse taps (the span would be
     // mostly unused bytes) and stay on the gather kernel.
     if ((row_bytes & 15u) || !aligned16(src) || p.scale_x > 6.0f || p.sw < 16u) return KB200_OK;
+    // developer knobs (tuning sweeps only): KB200_FR_NPX, KB200_FR_STAGES, KB200_FR_CTAS
+    static const int tune_npx = env_int("KB200_FR_NPX", 0), tune_stages = env_int("KB200_FR_STAGES", 0), tune_ctas = env_int("KB200_FR_CTAS", 0);
+    // columns per thread: least padding in the last tile (within 2 %); among equals prefer 2, then 3, 1, 4, 5 — the
+    // B200 sweep (profiles/r1_cfg2_fused_resize.md) has 2 columns/thread ahead: enough amortisation, many producers.
+    int npx = 1;
+    {
+        static const int order[5] = {2, 3, 1, 4, 5};
+        double best = 1e30;
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t tw = FR_CT * order[i];
+            const double waste = (double)((p.dw + tw - 1) / tw) * tw / (double)p.dw;
+            if (waste < best - 0.02) { best = waste; npx = order[i]; }
+        }
+        if (tune_npx >= 1 && tune_npx <= 5) npx = tune_npx;
+    }
+    const uint32_t TW = FR_CT * (uint32_t)npx;
+    const bool yz = axis_weights_all_zero(p.dh, p.sh, p.scale_y);
+    const bool xz = yz && axis_weights_all_zero(p.dw, p.sw, p.scale_x);
+    const int mode = xz ? FR_POINT : (yz ? FR_YZERO : FR_GENERAL);
     // span bound: x0(last) - x0(first) <= ceil((TW-1)*scale_x) + 1 pixels, + the +1 tap, + 16-B rounding both ends
-    const double span_px = (double)(FS_TW - 1) * (double)p.scale_x + 4.0;
+    const double span_px = (double)(TW - 1) * (double)p.scale_x + 4.0;
     uint32_t slot = (uint32_t)(span_px * 3.0) + 32u;
     slot = (slot + 127u) & ~127u;
     slot = std::min(slot, (row_bytes + 16u + 127u) & ~127u);  // +16: the 3-word tap read may run 8 B past the span
-    const size_t smem = (size_t)slot * 2 * FS_STAGES;
+    const uint32_t stage_bytes = slot * (mode == FR_GENERAL ? 2u : 1u);
+    // Ring sizing: the sweep's optimum keeps ~36 KB of source rows in flight per SM (about bandwidth x latency for the
+    // whole GPU); deeper rings or more CTAs than that cost 5-8 % (queueing in the memory system), fewer starve.
+    uint32_t stages = tune_stages >= 2 && tune_stages <= FR_MAX_STAGES ? (uint32_t)tune_stages : 3u;
+    int per_sm = tune_ctas > 0 ? tune_ctas : (int)std::lround(36.0 * 1024.0 / ((double)stages * stage_bytes));
+    per_sm = std::max(2, std::min(per_sm, 8));
+    while (per_sm > 2 && (size_t)per_sm * ((size_t)stages * stage_bytes + 1024) > 200 * 1024) --per_sm;
+    if (tune_ctas <= 0 && tune_stages <= 0 && per_sm == 2) stages = std::min<uint32_t>(FR_MAX_STAGES, std::max<uint32_t>(3u, (uint32_t)(18.0 * 1024.0 / stage_bytes)));
+    if (stages < 3) return KB200_OK;
+    const size_t smem = (size_t)stage_bytes * stages;
     if (smem > 200 * 1024) return KB200_OK;
-    static bool attr_done = false;  // idempotent; a benign race would set the same value twice
-    if (smem > 48 * 1024 && !attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(fused_resize_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-        attr_done = true;
-    }
-    FusedStagedParams P;
+
+    FusedRowsParams R;
+    FusedStagedParams& P = R.g;
     P.p = p;
-    P.tiles_x = (p.dw + FS_TW - 1) / FS_TW;
-    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (220 * 1024) / (smem + 1024)));
+    P.tiles_x = (p.dw + TW - 1) / TW;
     const size_t ctas = (size_t)device_info().sm_count * per_sm;
     // chunk height: enough units for ~16 per CTA (load balance) but at least 8 rows (amortise the x-side)
     const size_t total_rows = (size_t)p.dh * batch * P.tiles_x;
@@ -463,13 +541,20 @@ int launch_fused_resize_staged(cudaStream_t s, const uint8_t* src, float* dst, c
     P.nunits = (uint32_t)nunits;
     P.slot_bytes = slot;
     P.row_bytes = row_bytes;
+    R.stages = stages;
+    R.stage_bytes = stage_bytes;
     const unsigned grid = (unsigned)std::min<size_t>(nunits, ctas);
     P.dtx = grid % P.tiles_x;
     const uint32_t g = grid / P.tiles_x;
     P.dcy = g % P.chunks_y;
     P.dimg = g / P.chunks_y;
-    fused_resize_staged_kernel<<<grid, FS_THREADS, smem, s>>>(src, dst, P);
-    KB200_TRY(check_launch("fused_resize_staged_kernel"));
+    const bool allfma = p.fma_bulk >= p.dw;
+    cudaError_t e;
+    if (mode == FR_POINT) e = fr_launch_npx<FR_POINT>(npx, allfma, grid, smem, s, src, dst, R);
+    else if (mode == FR_YZERO) e = fr_launch_npx<FR_YZERO>(npx, allfma, grid, smem, s, src, dst, R);
+    else e = fr_launch_npx<FR_GENERAL>(npx, allfma, grid, smem, s, src, dst, R);
+    if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    KB200_TRY(check_launch("fused_rows_kernel"));
     *handled = true;
     return KB200_OK;
 }

@@ -55,9 +55,10 @@ elif op == "std_mean":
     u8 = kb.Image(torch.randint(0, 256, (32, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g))
     fn = lambda: kb.imgproc.std_mean_sums(u8)
 elif op == "cfg2":
-    src = torch.randint(0, 256, (16, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g)
+    nb = int(os.environ.get("KB_BATCH", "16"))
+    src = torch.randint(0, 256, (nb, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g)
     p = kb.imgproc.NormalizeParams.from_mean_std(MEAN, STD)
-    dst = torch.empty((16, 3, 720, 1280), dtype=torch.float32, device=dev)
+    dst = torch.empty((nb, 3, 720, 1280), dtype=torch.float32, device=dev)
     fn = lambda: kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(src, 1280, 720, p.scale, p.bias, out=dst)
 else:
     raise SystemExit(f"unknown op {op}")
