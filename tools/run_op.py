@@ -51,6 +51,10 @@ elif op in ("gauss", "sobel", "warp", "affine", "resize_f32", "gray", "normalize
         fn = lambda: kb.imgproc.gray_from_rgb(src, gray)
     else:
         fn = lambda: kb.imgproc.normalize_mean_std(src, dst, MEAN, STD)
+elif op == "rgb_nv12":
+    raw = torch.randint(0, 256, (64, 1920 * 1080 * 3 // 2), dtype=torch.uint8, device=dev, generator=g)
+    rgb = kb.Image.zeros_cuda(kb.ImageSize(1920, 1080), 3, torch.uint8, dev, batch=64)
+    fn = lambda: kb.imgproc.rgb_from_nv12(raw, rgb)
 elif op == "std_mean":
     u8 = kb.Image(torch.randint(0, 256, (32, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g))
     fn = lambda: kb.imgproc.std_mean_sums(u8)
