@@ -21,6 +21,12 @@ pub mod ffi {
 
     #[repr(C)]
     #[derive(Clone, Copy, Debug, Default)]
+    /// Opaque staging ring of the host-buffer entry points (include/kornia_b200.h, kb200_host_pipeline).
+    #[repr(C)]
+    pub struct kb200_host_pipeline {
+        _private: [u8; 0],
+    }
+
     pub struct kb200_preprocess_desc {
         pub scale_x: f32,
         pub scale_y: f32,
@@ -58,6 +64,20 @@ pub mod ffi {
         pub fn kb200_resize_normalize_chw_u8_f32(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut f32, dst_len: usize,
                                                  src_w: u32, src_h: u32, dst_w: u32, dst_h: u32, batch: u32, scale: *const f32,
                                                  bias: *const f32, leaf: c_int) -> c_int;
+        pub fn kb200_resize_row_plan(src_h: u32, dst_h: u32, period: *mut u32, first: *mut u32, keep: *mut u32);
+        pub fn kb200_resize_normalize_chw_u8_f32_rows(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut f32, dst_len: usize,
+                                                      src_w: u32, src_h: u32, dst_w: u32, dst_h: u32, batch: u32, scale: *const f32,
+                                                      bias: *const f32, leaf: c_int, row_period: u32, row_first: u32, row_keep: u32) -> c_int;
+        pub fn kb200_host_pipeline_create(device: c_int, src_chunk_bytes: usize, dst_chunk_bytes: usize, depth: c_int,
+                                          out: *mut *mut kb200_host_pipeline) -> c_int;
+        pub fn kb200_host_pipeline_destroy(pipeline: *mut kb200_host_pipeline);
+        pub fn kb200_host_pipeline_last_transfer(pipeline: *const kb200_host_pipeline, h2d_bytes: *mut u64, d2h_bytes: *mut u64) -> c_int;
+        pub fn kb200_host_register(ptr: *mut c_void, bytes: usize) -> c_int;
+        pub fn kb200_host_unregister(ptr: *mut c_void) -> c_int;
+        pub fn kb200_resize_normalize_chw_u8_f32_host(pipeline: *mut kb200_host_pipeline, stream: *mut c_void, host_src: *const u8,
+                                                      src_len: usize, host_dst: *mut f32, dst_len: usize, src_w: u32, src_h: u32,
+                                                      dst_w: u32, dst_h: u32, batch: u32, scale: *const f32, bias: *const f32,
+                                                      leaf: c_int) -> c_int;
         pub fn kb200_resize_bilinear_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32,
                                         src_h: u32, dst_w: u32, dst_h: u32, channels: u32, batch: u32) -> c_int;
         pub fn kb200_warp_affine_f32_c3(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize, src_w: u32,
@@ -126,6 +146,11 @@ fn bind(ctx: &Arc<CudaContext>) -> Result<(), Kb200Error> {
     // the reference launchers take `ctx` to compile/launch on the right device; here it selects the device
     check(unsafe { ffi::kb200_set_device(ctx.ordinal() as c_int) })
 }
+
+/// `leaf` argument of the fused resize / normalize entry points: which CPU leaf's rounding is reproduced.
+pub const LEAF_SCALAR: c_int = 0;
+pub const LEAF_X86_AVX2_FMA: c_int = 1;
+pub const LEAF_NEON: c_int = 2;
 
 /// `PixelMapping` of cuda/resize.rs:441.
 #[derive(Debug, Clone, Copy, PartialEq, Eq)]
@@ -224,4 +249,49 @@ pub fn launch_preprocess_batch_f32(
     check(unsafe {
         ffi::kb200_preprocess_f32(stream.cu_stream() as *mut c_void, desc, ptrs.as_ptr(), lens.as_ptr(), frames.len() as u32, dp as *mut f32, dst_len)
     })
+}
+
+
+/// Staging ring for the HOST-buffer form of `resize_normalize_to_tensor_u8_to_f32_bilinear` (resize/fused.rs:147):
+/// host `&Image<u8,3>` in, host CHW tensor out, executed on the GPU.  One per device; calls only enqueue.
+pub struct HostPipeline {
+    raw: *mut ffi::kb200_host_pipeline,
+}
+
+// SAFETY: the pipeline owns CUDA streams/buffers that may be used from any thread; calls are serialised by &mut self.
+unsafe impl Send for HostPipeline {}
+
+impl HostPipeline {
+    pub fn new(device: usize, src_chunk_bytes: usize, dst_chunk_bytes: usize, depth: usize) -> Result<Self, Kb200Error> {
+        let mut raw = std::ptr::null_mut();
+        check(unsafe { ffi::kb200_host_pipeline_create(device as c_int, src_chunk_bytes, dst_chunk_bytes, depth as c_int, &mut raw) })?;
+        Ok(Self { raw })
+    }
+
+    /// `src`: `batch` tightly packed HWC u8 images; `dst`: [batch, 3, dst_h, dst_w] f32.  Both should be page-locked.
+    /// Enqueue-only: synchronise `stream` before reading `dst`.
+    #[allow(clippy::too_many_arguments)]
+    pub fn resize_normalize_u8_to_f32(
+        &mut self, stream: &Arc<CudaStream>, src: &[u8], src_size: (u32, u32), dst: &mut [f32], dst_size: (u32, u32), batch: u32,
+        scale: &[f32; 3], bias: &[f32; 3],
+    ) -> Result<(), Kb200Error> {
+        check(unsafe {
+            ffi::kb200_resize_normalize_chw_u8_f32_host(self.raw, stream.cu_stream() as *mut c_void, src.as_ptr(), src.len(),
+                                                        dst.as_mut_ptr(), dst.len(), src_size.0, src_size.1, dst_size.0, dst_size.1,
+                                                        batch, scale.as_ptr(), bias.as_ptr(), LEAF_X86_AVX2_FMA)
+        })
+    }
+
+    /// (uploaded, downloaded) bytes of the last call — uploads count only the source rows the geometry taps.
+    pub fn last_transfer(&self) -> Result<(u64, u64), Kb200Error> {
+        let (mut up, mut down) = (0u64, 0u64);
+        check(unsafe { ffi::kb200_host_pipeline_last_transfer(self.raw, &mut up, &mut down) })?;
+        Ok((up, down))
+    }
+}
+
+impl Drop for HostPipeline {
+    fn drop(&mut self) {
+        unsafe { ffi::kb200_host_pipeline_destroy(self.raw) }
+    }
 }
