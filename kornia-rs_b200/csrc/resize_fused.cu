@@ -111,7 +111,7 @@ void resize_row_plan(uint32_t sh, uint32_t dh, uint32_t* period, uint32_t* first
 
 int launch_fused_resize(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch) {
     const bool box2x = (p.sw == 2 * p.dw && p.sh == 2 * p.dh);
-    if (!box2x) {
+    {
         bool handled = false;
         KB200_TRY(launch_fused_resize_rows(s, src, dst, p, batch, &handled));
         if (handled) return KB200_OK;
@@ -287,13 +287,16 @@ struct UnitWalk {
 //               the consumer then multiplies stale-but-finite bytes by 0, which is exact).
 //   FR_YZERO    every destination row has wy == 0 (odd integer vertical ratio, or 1:1): one source row per stage.
 //   FR_POINT    additionally every column has wx == 0: out = byte * scale + bias — three byte loads per pixel.
+//   FR_BOX      exact 2x downscale (resize/fused.rs:57-127): the integer sum of the 2x2 block times scale/4.  The
+//               half-pixel sampler at scale 2 taps exactly the block's rows and columns (x0 = 2d, y0 = 2d), so the
+//               staging is the general one; the four byte sums per channel are IDP4A dot products with 0/1 masks.
 //
 // A right-edge column (x1 == x0) is folded into the general arithmetic by forcing wx = 0: b == a there, so
 // a + wx*(b-a) == a for any wx, and with wx = 0 the (finite) neighbour byte that is read instead contributes ±0.
 static constexpr int FR_CT = 128;               // consumer threads per CTA
 static constexpr int FR_THREADS = FR_CT + 32;   // + producer warp
 static constexpr int FR_MAX_STAGES = 16;
-enum { FR_GENERAL = 0, FR_YZERO = 1, FR_POINT = 2 };
+enum { FR_GENERAL = 0, FR_YZERO = 1, FR_POINT = 2, FR_BOX = 3 };
 
 struct FusedRowsParams {
     FusedStagedParams g;   // geometry + unit walk (tiles_x counts tiles of FR_CT*NPX columns)
@@ -305,6 +308,22 @@ template <int MODE>
 __device__ __forceinline__ void fr_pixel(const uint8_t* __restrict__ rp, uint32_t slot_bytes, uint32_t shft, float wx, float wy, bool fma_leaf,
                                          float s0, float s1, float s2, float o0, float o1, float o2, float& q0, float& q1, float& q2) {
     float v[3];
+    if (MODE == FR_BOX) {
+        const uint32_t* r0 = reinterpret_cast<const uint32_t*>(rp);
+        const uint32_t* r1 = reinterpret_cast<const uint32_t*>(rp + slot_bytes);
+        const uint32_t a0 = r0[0], a1 = r0[1], a2 = r0[2], c0 = r1[0], c1 = r1[1], c2 = r1[2];
+        const uint32_t lo0 = __funnelshift_r(a0, a1, shft), hi0 = __funnelshift_r(a1, a2, shft);  // r0 g0 b0 r1 | g1 b1 . .
+        const uint32_t lo1 = __funnelshift_r(c0, c1, shft), hi1 = __funnelshift_r(c1, c2, shft);
+        // sums of resize/fused.rs:543-548: u32 adds of four bytes — exact, order-free
+        const uint32_t sr = __dp4a(lo0, 0x01000001u, __dp4a(lo1, 0x01000001u, 0u));
+        const uint32_t sg = __dp4a(lo0, 0x00000100u, __dp4a(hi0, 0x00000001u, __dp4a(lo1, 0x00000100u, __dp4a(hi1, 0x00000001u, 0u))));
+        const uint32_t sb = __dp4a(lo0, 0x00010000u, __dp4a(hi0, 0x00000100u, __dp4a(lo1, 0x00010000u, __dp4a(hi1, 0x00000100u, 0u))));
+        // s0..s2 carry scale[c] * 0.25f here (formed once per thread, the reference forms it once per row)
+        const float fr = (float)sr, fg = (float)sg, fb = (float)sb;
+        if (fma_leaf) { q0 = fmaf(fr, s0, o0); q1 = fmaf(fg, s1, o1); q2 = fmaf(fb, s2, o2); }
+        else          { q0 = fr * s0 + o0;     q1 = fg * s1 + o1;     q2 = fb * s2 + o2; }
+        return;
+    }
     if (MODE == FR_POINT) {
         v[0] = (float)rp[0]; v[1] = (float)rp[1]; v[2] = (float)rp[2];
     } else {
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(FR_THREADS) fused_rows_kernel(const uint8_t* _
                 float wy;
                 fused_axis(dy, p.scale_y, p.sh, &y0, &y1, &wy);
                 uint8_t* sbase = smem_raw + (size_t)stage * R.stage_bytes;
-                const bool two = (MODE == FR_GENERAL) && (wy != 0.0f);  // a zero-weight y1 row is never fetched
+                const bool two = (MODE == FR_BOX) || ((MODE == FR_GENERAL) && (wy != 0.0f));  // a zero-weight y1 row is never fetched
                 if (MODE == FR_GENERAL) wy_s[stage] = wy;  // before the arrive(release): covered by the consumers' acquire on `full`
                 mbar_expect_tx(&full_bar[stage], two ? bytes * 2u : bytes);
                 tma_load_1d(sbase, frame + (size_t)fused_row_slot(p, y0) * P.row_bytes, bytes, &full_bar[stage]);
@@ -395,7 +414,8 @@ __global__ void __launch_bounds__(FR_THREADS) fused_rows_kernel(const uint8_t* _
     }
 
     // ── consumer warps ──
-    const float s0 = p.scale[0], s1 = p.scale[1], s2 = p.scale[2];
+    const float qs = (MODE == FR_BOX) ? 0.25f : 1.0f;   // box: scale[c] * 0.25f (resize/fused.rs:541); x * 1.0f is exact
+    const float s0 = p.scale[0] * qs, s1 = p.scale[1] * qs, s2 = p.scale[2] * qs;
     const float o0 = p.bias[0], o1 = p.bias[1], o2 = p.bias[2];
     const bool lane0 = (tid & 31u) == 0;
     for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x, w.advance(P)) {
@@ -507,13 +527,14 @@ int launch_fused_resize_rows(cudaStream_t s, const uint8_t* src, float* dst, con
     const uint32_t TW = FR_CT * (uint32_t)npx;
     const bool yz = axis_weights_all_zero(p.dh, p.sh, p.scale_y);
     const bool xz = yz && axis_weights_all_zero(p.dw, p.sw, p.scale_x);
-    const int mode = xz ? FR_POINT : (yz ? FR_YZERO : FR_GENERAL);
+    const bool box2x = (p.sw == 2 * p.dw && p.sh == 2 * p.dh);
+    const int mode = box2x ? FR_BOX : (xz ? FR_POINT : (yz ? FR_YZERO : FR_GENERAL));
     // span bound: x0(last) - x0(first) <= ceil((TW-1)*scale_x) + 1 pixels, + the +1 tap, + 16-B rounding both ends
     const double span_px = (double)(TW - 1) * (double)p.scale_x + 4.0;
     uint32_t slot = (uint32_t)(span_px * 3.0) + 32u;
     slot = (slot + 127u) & ~127u;
     slot = std::min(slot, (row_bytes + 16u + 127u) & ~127u);  // +16: the 3-word tap read may run 8 B past the span
-    const uint32_t stage_bytes = slot * (mode == FR_GENERAL ? 2u : 1u);
+    const uint32_t stage_bytes = slot * ((mode == FR_GENERAL || mode == FR_BOX) ? 2u : 1u);
     // Ring sizing: the sweep's optimum keeps ~36 KB of source rows in flight per SM (about bandwidth x latency for the
     // whole GPU); deeper rings or more CTAs than that cost 5-8 % (queueing in the memory system), fewer starve.
     uint32_t stages = tune_stages >= 2 && tune_stages <= FR_MAX_STAGES ? (uint32_t)tune_stages : 3u;
@@ -552,6 +573,7 @@ int launch_fused_resize_rows(cudaStream_t s, const uint8_t* src, float* dst, con
     cudaError_t e;
     if (mode == FR_POINT) e = fr_launch_npx<FR_POINT>(npx, allfma, grid, smem, s, src, dst, R);
     else if (mode == FR_YZERO) e = fr_launch_npx<FR_YZERO>(npx, allfma, grid, smem, s, src, dst, R);
+    else if (mode == FR_BOX) e = fr_launch_npx<FR_BOX>(npx, allfma, grid, smem, s, src, dst, R);
     else e = fr_launch_npx<FR_GENERAL>(npx, allfma, grid, smem, s, src, dst, R);
     if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     KB200_TRY(check_launch("fused_rows_kernel"));

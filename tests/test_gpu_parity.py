@@ -147,7 +147,9 @@ FUSED_CASES = [(60, 40, 37, 23), (74, 10, 37, 5), (384, 216, 128, 72), (128, 72,
                (256, 64, 100, 30), (512, 40, 171, 13), (1024, 30, 1000, 29), (1600, 21, 300, 9), (640, 18, 1279, 35),
                (1920, 27, 1281, 19), (48, 9, 50, 10), (16, 16, 3, 3),
                # integer downscales: odd ratios have a vertical weight of exactly 0 (single-row staging), even ones 0.5
-               (160, 45, 32, 9), (320, 35, 64, 5), (256, 64, 64, 16), (96, 63, 80, 21), (768, 36, 256, 9), (1280, 30, 1280, 10)]
+               (160, 45, 32, 9), (320, 35, 64, 5), (256, 64, 64, 16), (96, 63, 80, 21), (768, 36, 256, 9), (1280, 30, 1280, 10),
+               # exact 2x (box average) on 16-byte-aligned rows: the staged box mode, full / ragged / multi-tile widths
+               (256, 64, 128, 32), (96, 20, 48, 10), (3840, 16, 1920, 8), (1312, 12, 656, 6), (544, 10, 272, 5)]
 
 
 @pytest.mark.parametrize("sw,sh,dw,dh", FUSED_CASES)
