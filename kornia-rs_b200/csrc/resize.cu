@@ -116,6 +116,68 @@ __device__ __forceinline__ void bilinear_tap_q14(uint32_t i, double scale, uint3
     *ofs = (uint32_t)i0;
 }
 
+// ── u8 kernels of resize_fast_u8_aa (resize/mod.rs:283-410) ──────────────────────────────────
+// Thread per destination pixel (pyrup: per 2x2 destination block) with byte loads: a warp's pixels read one
+// contiguous byte run per source row and L1 turns the byte loads into whole sectors.  A variant that gave each thread
+// four consecutive destination BYTES (one STG.32) and re-evaluated the per-pixel setup per byte measured 1.5-1.8x
+// slower on B200: these kernels are bound by instructions per pixel, not by the byte stores.
+
+// resize/kernels.rs:64-75: dst = (a + b + c + d + 2) >> 2 per channel
+__global__ void __launch_bounds__(256) pyrdown_2x_rgb_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sw * sh * 3;
+    uint8_t* d = dst + ((size_t)blockIdx.z * dw * dh + (size_t)y * dw + x) * 3;
+    const uint8_t* r0 = s + ((size_t)(2 * y) * sw + 2 * x) * 3;
+    const uint8_t* r1 = r0 + (size_t)sw * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) d[ch] = (uint8_t)(((uint32_t)r0[ch] + r0[3 + ch] + r1[ch] + r1[3 + ch] + 2u) >> 2);
+}
+
+// resize/kernels.rs:168-181 + :274-281 + resize/pyramid.rs:50-120.
+// Horizontal stage H(row)[X]: X = 2j+1 -> (a + avg + 1) >> 1, X = 2j+2 -> (b + avg + 1) >> 1 with a = row[j], b = row[j+1],
+// avg = (a + b + 1) >> 1; X = 0 and X = 2sw-1 copy the edge pixel.  Vertical stage: row 2I+1 -> blend(H(I), H(I+1)),
+// row 2I+2 -> blend(H(I+1), H(I)), blend(p, q) = (p + ((p + q + 1) >> 1) + 1) >> 1; rows 0 and 2sh-1 are H of the edge row.
+// One thread per (j, I) in [-1, sw-1] x [-1, sh-1] produces the 2x2 destination block X in {2j+1, 2j+2}, Y in {2I+1, 2I+2}
+// from the four source pixels it shares.  The edges need no special case: with the index clamped, a == b gives
+// avg = a and (a + a + 1) >> 1 = a, i.e. exactly the copied edge pixel / edge row of the reference.
+__global__ void __launch_bounds__(256) pyrup_2x_rgb_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                              uint32_t sw, uint32_t sh) {
+    const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x) - 1;
+    const int I = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
+    if (j > (int)sw - 1 || I > (int)sh - 1) return;
+    const uint32_t dw = 2 * sw;
+    const uint8_t* s = src + (size_t)blockIdx.z * sw * sh * 3;
+    uint8_t* d = dst + (size_t)blockIdx.z * dw * (2 * sh) * 3;
+    const uint32_t ja = (uint32_t)max(j, 0), jb = (uint32_t)min(j + 1, (int)sw - 1);
+    const uint32_t Ia = (uint32_t)max(I, 0), Ib = (uint32_t)min(I + 1, (int)sh - 1);
+    const uint8_t* ra = s + (size_t)Ia * sw * 3;
+    const uint8_t* rb = s + (size_t)Ib * sw * 3;
+    const bool x_odd = j >= 0, x_even = j + 1 < (int)sw;     // X = 2j+1 / X = 2j+2 inside the row
+    const bool y_top = I >= 0, y_bot = I + 1 < (int)sh;      // Y = 2I+1 / Y = 2I+2 inside the image
+    uint8_t* d_top = d + ((size_t)(2 * I + 1) * dw + (size_t)(2 * j + 1)) * 3;   // only dereferenced where valid
+    uint8_t* d_bot = d_top + (size_t)dw * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const uint32_t a0 = ra[ja * 3 + ch], b0 = ra[jb * 3 + ch], a1 = rb[ja * 3 + ch], b1 = rb[jb * 3 + ch];
+        const uint32_t avg0 = (a0 + b0 + 1u) >> 1, avg1 = (a1 + b1 + 1u) >> 1;
+        const uint32_t hao = (a0 + avg0 + 1u) >> 1, hae = (b0 + avg0 + 1u) >> 1;   // H(Ia) at X odd / even
+        const uint32_t hbo = (a1 + avg1 + 1u) >> 1, hbe = (b1 + avg1 + 1u) >> 1;   // H(Ib)
+        const uint32_t mo = (hao + hbo + 1u) >> 1, me = (hae + hbe + 1u) >> 1;
+        if (y_top) {
+            if (x_odd) d_top[ch] = (uint8_t)((hao + mo + 1u) >> 1);
+            if (x_even) d_top[3 + ch] = (uint8_t)((hae + me + 1u) >> 1);
+        }
+        if (y_bot) {
+            if (x_odd) d_bot[ch] = (uint8_t)((hbo + mo + 1u) >> 1);
+            if (x_even) d_bot[3 + ch] = (uint8_t)((hbe + me + 1u) >> 1);
+        }
+    }
+}
+
+// resize/bilinear.rs:70 + resize/kernels.rs:1141-1166 — Q14 bilinear, taps from the f64 expression (bilinear_tap_q14).
 template <int C>
 __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                                  uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh,
@@ -139,6 +201,30 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* 
         const unsigned long long top = p00 * fx1 + p01 * fx;
         const unsigned long long bot = p10 * fx1 + p11 * fx;
         d[ch] = (uint8_t)((top * fy1 + bot * (unsigned long long)fy + (1ull << 27)) >> 28);
+    }
+}
+
+// resize/nearest.rs:18-21: clamp(floor((i + 0.5) * scale)) in f64
+__device__ __forceinline__ uint32_t nearest_index_f64(uint32_t i, double scale, uint32_t src_len) {
+    const long long v = (long long)floor(__dmul_rn((double)i + 0.5, scale));
+    return (uint32_t)min(max(v, 0ll), (long long)src_len - 1);
+}
+template <int C>
+__global__ void __launch_bounds__(256) resize_nearest_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t sw,
+                                                                uint32_t sh, uint32_t dw, uint32_t dh, uint32_t Cdyn, double scale_x,
+                                                                double scale_y) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh) return;
+    const uint32_t Cn = C > 0 ? (uint32_t)C : Cdyn;
+    const uint32_t xi = nearest_index_f64(x, scale_x, sw), yi = nearest_index_f64(y, scale_y, sh);
+    const uint8_t* p = src + ((size_t)blockIdx.z * sw * sh + (size_t)yi * sw + xi) * Cn;
+    uint8_t* d = dst + ((size_t)blockIdx.z * dw * dh + (size_t)y * dw + x) * Cn;
+    if (C > 0) {
+#pragma unroll
+        for (int ch = 0; ch < (C > 0 ? C : 1); ++ch) d[ch] = p[ch];
+    } else {
+        for (uint32_t ch = 0; ch < Cn; ++ch) d[ch] = p[ch];
     }
 }
 
@@ -239,6 +325,39 @@ KB200_API int kb200_resize_bilinear_u8(kb200_stream_t stream, const uint8_t* src
     else if (C == 3) resize_bilinear_u8_kernel<3><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
     else resize_bilinear_u8_kernel<4><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
     return check_launch("resize_bilinear_u8_kernel");
+}
+
+
+/* resize/mod.rs:348 resize_fast_u8_aa for Nearest / Bilinear — the reference's path selection (resize_u8_path, :283-337):
+ * exact 2x down / up on RGB take the pyramid arms, Nearest works for any channel count, Bilinear is the Q14 arm. */
+KB200_API int kb200_resize_fast_u8(kb200_stream_t stream, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len,
+                                   uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, uint32_t C, uint32_t batch, int interp) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_geometry(sw, sh, dw, dh, batch)); KB200_TRY(check_batch(batch));
+    if (C == 0) return fail(KB200_ERR_UNSUPPORTED, "channel count must be at least 1");
+    KB200_TRY(check_slice("dst", dst_len, (size_t)dw * dh * C * batch));
+    KB200_TRY(check_slice("src", src_len, (size_t)sw * sh * C * batch));
+    cudaStream_t s = as_stream(stream);
+    dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
+    if (interp == KB200_INTERP_BILINEAR && C == 3 && sw == 2 * dw && sh == 2 * dh && sw >= 2 && sh >= 2) {
+        pyrdown_2x_rgb_u8_kernel<<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh);
+        return check_launch("pyrdown_2x_rgb_u8_kernel");
+    }
+    if (interp == KB200_INTERP_BILINEAR && C == 3 && dw == 2 * sw && dh == 2 * sh && sw >= 2 && sh >= 2) {
+        dim3 ugrid(div_up(sw + 1, 32), div_up(sh + 1, 8), batch);   // (j, I) in [-1, sw-1] x [-1, sh-1]
+        pyrup_2x_rgb_u8_kernel<<<ugrid, block, 0, s>>>(src, dst, sw, sh);
+        return check_launch("pyrup_2x_rgb_u8_kernel");
+    }
+    if (interp == KB200_INTERP_NEAREST) {
+        const double scale_x = (double)sw / (double)dw, scale_y = (double)sh / (double)dh;
+        if (C == 1) resize_nearest_u8_kernel<1><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, C, scale_x, scale_y);
+        else if (C == 3) resize_nearest_u8_kernel<3><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, C, scale_x, scale_y);
+        else if (C == 4) resize_nearest_u8_kernel<4><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, C, scale_x, scale_y);
+        else resize_nearest_u8_kernel<0><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, C, scale_x, scale_y);
+        return check_launch("resize_nearest_u8_kernel");
+    }
+    if (interp == KB200_INTERP_BILINEAR) return kb200_resize_bilinear_u8(stream, src, src_len, dst, dst_len, sw, sh, dw, dh, C, batch);
+    return fail(KB200_ERR_UNSUPPORTED, "resize_fast_u8: interpolation mode %d is not built (Nearest and Bilinear are)", interp);
 }
 
 }  // extern "C"

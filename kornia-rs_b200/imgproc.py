@@ -93,20 +93,25 @@ def resize_bilinear_normalize(src: Image, dst: Image, mean: Sequence[float], std
 
 
 def resize_fast_u8(src: Image, dst: Image, interpolation: InterpolationMode = InterpolationMode.Bilinear) -> None:
-    """resize/mod.rs:348 `resize_fast_u8_aa` — the generic Q14 bilinear arm (resize/bilinear.rs:70).
-    The exact-2x pyramid arms and nearest/bicubic/lanczos are "next" rows (SURVEY §8(f) #1)."""
-    if interpolation != InterpolationMode.Bilinear:
+    """resize/mod.rs:348 `resize_fast_u8_aa` with the reference's path selection (`resize_u8_path`, :283-337): exact 2x
+    down / up on RGB → pyramid arms, Nearest → any channel count, Bilinear → Q14 (C ∈ {1,3,4}, source ≥ 2x2).
+    Bicubic / Lanczos (the antialiased separable arm) are not built."""
+    if interpolation not in (InterpolationMode.Bilinear, InterpolationMode.Nearest):
         raise ImageError.UnsupportedInterpolation(interpolation)
     dev = _prep("resize_fast_u8", src, dst)
     _expect_dtype(src, torch.uint8, "src"); _expect_dtype(dst, torch.uint8, "dst")
     c = src.num_channels()
-    if c not in (1, 3, 4):
-        raise ImageError.UnsupportedChannelCount(c)
-    if src.cols() < 2 or src.rows() < 2:
-        raise ImageError.InvalidImageSize(src.cols(), src.rows(), 2, 2)
+    sw, sh, dw, dh = src.cols(), src.rows(), dst.cols(), dst.rows()
+    pyr = c == 3 and sw >= 2 and sh >= 2 and ((sw == 2 * dw and sh == 2 * dh) or (dw == 2 * sw and dh == 2 * sh))
+    if interpolation == InterpolationMode.Bilinear and not pyr:
+        if c not in (1, 3, 4):
+            raise ImageError.UnsupportedChannelCount(c)
+        if sw < 2 or sh < 2:
+            raise ImageError.InvalidImageSize(sw, sh, 2, 2)
     n = _same_batch(src, dst)
-    _check(_lib.lib().kb200_resize_bilinear_u8(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(),
-                                               dst.numel(), src.cols(), src.rows(), dst.cols(), dst.rows(), c, n))
+    code = 1 if interpolation == InterpolationMode.Bilinear else 0
+    _check(_lib.lib().kb200_resize_fast_u8(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
+                                           sw, sh, dw, dh, c, n, code))
 
 
 class NormalizeParams:

@@ -437,6 +437,91 @@ KO_API int ko_resize_bilinear_u8(const uint8_t* src, size_t sw, size_t sh, uint8
 }
 
 // ─────────────────────────────────────────────────────────────────────────────
+// §8(f)#1 — the other arms of resize_fast_u8_aa (resize/mod.rs:283-410): exact-2x pyramid paths and nearest.
+// ─────────────────────────────────────────────────────────────────────────────
+
+// resize/pyramid.rs:18-45 + resize/kernels.rs:64-75 (pyrdown_row_rgb_u8_scalar): rounded mean of each 2x2 block.
+KO_API void ko_pyrdown_2x_rgb_u8(const uint8_t* src, size_t sw, size_t sh, uint8_t* dst) {
+    const size_t dw = sw / 2, dh = sh / 2, ss = sw * 3, ds = dw * 3;
+    for (size_t y = 0; y < dh; ++y) {
+        const uint8_t* r0 = src + (2 * y) * ss;
+        const uint8_t* r1 = src + (2 * y + 1) * ss;
+        uint8_t* d = dst + y * ds;
+        for (size_t x = 0; x < dw; ++x)
+            for (size_t ch = 0; ch < 3; ++ch) {
+                const uint16_t sum = (uint16_t)(r0[(2 * x) * 3 + ch] + r0[(2 * x + 1) * 3 + ch] + r1[(2 * x) * 3 + ch] + r1[(2 * x + 1) * 3 + ch]);
+                d[x * 3 + ch] = (uint8_t)((sum + 2) >> 2);
+            }
+    }
+}
+
+// resize/kernels.rs:168-181 (hinterp_row_rgb_u8_scalar)
+static void hinterp_row_rgb_u8(const uint8_t* src, uint8_t* dst, size_t sw) {
+    for (size_t ch = 0; ch < 3; ++ch) dst[ch] = src[ch];
+    for (size_t j = 0; j + 1 < sw; ++j)
+        for (size_t ch = 0; ch < 3; ++ch) {
+            const uint16_t a = src[j * 3 + ch], b = src[(j + 1) * 3 + ch];
+            const uint16_t avg = (uint16_t)((a + b + 1) >> 1);
+            dst[(2 * j + 1) * 3 + ch] = (uint8_t)((a + avg + 1) >> 1);
+            dst[(2 * j + 2) * 3 + ch] = (uint8_t)((b + avg + 1) >> 1);
+        }
+    const size_t tail = (2 * sw - 1) * 3;
+    for (size_t ch = 0; ch < 3; ++ch) dst[tail + ch] = src[(sw - 1) * 3 + ch];
+}
+// resize/kernels.rs:274-281 (blend_75_25_row_scalar): round(0.75 a + 0.25 b) as two rounding half-adds
+static void blend_75_25_row(const uint8_t* a, const uint8_t* b, uint8_t* dst, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint16_t av = a[i], bv = b[i];
+        const uint16_t avg = (uint16_t)((av + bv + 1) >> 1);
+        dst[i] = (uint8_t)((av + avg + 1) >> 1);
+    }
+}
+// resize/pyramid.rs:50-120: rows 0 and 2h-1 are horizontally interpolated edge rows; block I writes rows 2I+1, 2I+2.
+KO_API void ko_pyrup_2x_rgb_u8(const uint8_t* src, size_t sw, size_t sh, uint8_t* dst) {
+    const size_t dw = sw * 2, ss = sw * 3, ds = dw * 3;
+    hinterp_row_rgb_u8(src, dst, sw);
+    hinterp_row_rgb_u8(src + (sh - 1) * ss, dst + (2 * sh - 1) * ds, sw);
+    std::vector<uint8_t> ha(ds), hb(ds);
+    if (sh >= 2) hinterp_row_rgb_u8(src, ha.data(), sw);
+    for (size_t i = 0; i + 1 < sh; ++i) {
+        hinterp_row_rgb_u8(src + (i + 1) * ss, hb.data(), sw);
+        blend_75_25_row(ha.data(), hb.data(), dst + (2 * i + 1) * ds, ds);
+        blend_75_25_row(hb.data(), ha.data(), dst + (2 * i + 2) * ds, ds);
+        ha.swap(hb);
+    }
+}
+
+// resize/nearest.rs:18-21: clamp(floor((i + 0.5) * scale)) in f64 — pixel centre then floor, no -0.5
+static size_t nearest_index(size_t i, double scale, size_t src_len) {
+    long long v = (long long)std::floor(((double)i + 0.5) * scale);
+    if (v < 0) v = 0;
+    if (v > (long long)src_len - 1) v = (long long)src_len - 1;
+    return (size_t)v;
+}
+// resize/nearest.rs:42-78
+KO_API void ko_resize_nearest_u8(const uint8_t* src, size_t sw, size_t sh, uint8_t* dst, size_t dw, size_t dh, size_t C) {
+    const double sy = (double)sh / (double)dh, sx = (double)sw / (double)dw;
+    std::vector<size_t> xmap(dw);
+    for (size_t x = 0; x < dw; ++x) xmap[x] = nearest_index(x, sx, sw);
+    for (size_t y = 0; y < dh; ++y) {
+        const uint8_t* srow = src + nearest_index(y, sy, sh) * sw * C;
+        uint8_t* drow = dst + y * dw * C;
+        for (size_t x = 0; x < dw; ++x)
+            for (size_t ch = 0; ch < C; ++ch) drow[x * C + ch] = srow[xmap[x] * C + ch];
+    }
+}
+
+// resize/mod.rs:283-410 — path selection of resize_fast_u8_aa for Nearest / Bilinear.
+// interp: 0 = Nearest, 1 = Bilinear.  Returns 0, -1 (UnsupportedChannelCount), -2 (InvalidImageSize 2x2), -3 (mode not covered).
+KO_API int ko_resize_fast_u8(const uint8_t* src, size_t sw, size_t sh, uint8_t* dst, size_t dw, size_t dh, size_t C, int interp) {
+    if (interp == 1 && C == 3 && sw == dw * 2 && sh == dh * 2 && sw >= 2 && sh >= 2) { ko_pyrdown_2x_rgb_u8(src, sw, sh, dst); return 0; }
+    if (interp == 1 && C == 3 && dw == sw * 2 && dh == sh * 2 && sw >= 2 && sh >= 2) { ko_pyrup_2x_rgb_u8(src, sw, sh, dst); return 0; }
+    if (interp == 0) { ko_resize_nearest_u8(src, sw, sh, dst, dw, dh, C); return 0; }
+    if (interp == 1) return ko_resize_bilinear_u8(src, sw, sh, dst, dw, dh, C);
+    return -3;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
 // a4: warp_affine — warp/affine.rs:18-38 (invert), :70-79 (rotation matrix),
 // :123-366 (warp), warp/span.rs:36-81 (valid span).
 // ─────────────────────────────────────────────────────────────────────────────

@@ -66,6 +66,8 @@ def _declare(l: C.CDLL) -> None:
     l.ko_normalize_params_from_mean_std.argtypes = [vp, vp, vp, vp]
     l.ko_resize_normalize_u8_to_f32_chw_bilinear.argtypes = [vp, sz, sz, vp, sz, sz, vp, vp, i]
     l.ko_resize_bilinear_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz]
+    l.ko_resize_fast_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, C.c_int]
+    l.ko_resize_fast_u8.restype = C.c_int
     l.ko_invert_affine_transform.argtypes = [vp, vp]
     l.ko_get_rotation_matrix2d.argtypes = [f, f, f, f, vp]
     l.ko_constrain_span.argtypes = [f, f, i, f, C.c_longlong, C.c_longlong, vp, vp]
@@ -195,6 +197,18 @@ def resize_bilinear_u8(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
     rc = lib().ko_resize_bilinear_u8(_p(src), sw, sh, _p(dst), dw, dh, c)
     if rc != 0:
         raise ValueError(f"resize_bilinear_u8 rc={rc}")
+    return dst
+
+
+def resize_fast_u8(src: np.ndarray, dw: int, dh: int, interp: int = 1) -> np.ndarray:
+    """resize_fast_u8_aa path selection (resize/mod.rs:283-410): interp 0 = Nearest, 1 = Bilinear (exact-2x pyramid arms,
+    Q14 generic arm).  Raises ValueError with the reference's error class name."""
+    src = np.ascontiguousarray(src, np.uint8)
+    sh, sw, c = src.shape
+    dst = np.zeros((dh, dw, c), np.uint8)
+    rc = lib().ko_resize_fast_u8(_p(src), sw, sh, _p(dst), dw, dh, c, interp)
+    if rc != 0:
+        raise ValueError({-1: "UnsupportedChannelCount", -2: "InvalidImageSize", -3: "UnsupportedInterpolation"}.get(rc, str(rc)))
     return dst
 
 

@@ -240,6 +240,37 @@ def test_resize_bilinear_u8_q14(kb, oracle, dev, sw, sh, dw, dh, c):
     np.testing.assert_array_equal(dst.numpy(), oracle.resize_bilinear_u8(src, dw, dh))
 
 
+U8_FAST = [  # (sw, sh, dw, dh, c, mode)  mode: 1 = Bilinear, 0 = Nearest
+    (64, 48, 32, 24, 3, 1), (2, 2, 1, 1, 3, 1), (130, 6, 65, 3, 3, 1), (3840, 8, 1920, 4, 3, 1),          # pyrdown arm
+    (2, 2, 4, 4, 3, 1), (3, 4, 6, 8, 3, 1), (17, 9, 34, 18, 3, 1), (33, 6, 66, 12, 3, 1), (640, 5, 1280, 10, 3, 1),   # pyrup arm
+    (64, 48, 32, 24, 1, 1), (64, 48, 32, 24, 4, 1), (13, 9, 7, 5, 3, 1),                                     # 2x but not RGB / generic → Q14 arm
+    (7, 5, 3, 2, 3, 0), (5, 5, 9, 7, 1, 0), (64, 48, 1, 1, 4, 0), (1, 1, 8, 8, 2, 0), (23, 37, 11, 17, 5, 0), (1920, 9, 640, 3, 3, 0),
+]
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh,c,mode", U8_FAST)
+def test_resize_fast_u8_cascade(kb, oracle, dev, sw, sh, dw, dh, c, mode):
+    """resize_fast_u8_aa path selection (exact-2x pyramid arms, nearest, Q14) — bit-exact, batched."""
+    n = 3
+    src = np.stack([oracle.pattern_u8(sw * sh * c, 0xABCD + i).reshape(sh, sw, c) for i in range(n)])
+    want = np.stack([oracle.resize_fast_u8(src[i], dw, dh, mode) for i in range(n)])
+    s_img = kb.Image(cu(src, dev))
+    d_img = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), c, torch.uint8, dev, batch=n)
+    kb.imgproc.resize_fast_u8(s_img, d_img, kb.InterpolationMode.Bilinear if mode else kb.InterpolationMode.Nearest)
+    np.testing.assert_array_equal(d_img.numpy(), want)
+
+
+def test_resize_fast_u8_errors(kb, dev):
+    d = kb.Image.zeros_cuda(kb.ImageSize(3, 3), 2, torch.uint8, dev)
+    with pytest.raises(kb.ImageError, match="Unsupported channel count 2"):
+        kb.imgproc.resize_fast_u8(kb.Image.zeros_cuda(kb.ImageSize(4, 4), 2, torch.uint8, dev), d)
+    d3 = kb.Image.zeros_cuda(kb.ImageSize(3, 3), 3, torch.uint8, dev)
+    with pytest.raises(kb.ImageError, match="Invalid image size"):
+        kb.imgproc.resize_fast_u8(kb.Image.zeros_cuda(kb.ImageSize(1, 4), 3, torch.uint8, dev), d3)
+    with pytest.raises(kb.ImageError):
+        kb.imgproc.resize_fast_u8(kb.Image.zeros_cuda(kb.ImageSize(4, 4), 3, torch.uint8, dev), d3, kb.InterpolationMode.Bicubic)
+
+
 # ── warps ────────────────────────────────────────────────────────────────────
 AFFINES = [
     ("identity", [1, 0, 0, 0, 1, 0]),

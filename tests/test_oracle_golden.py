@@ -526,3 +526,59 @@ def test_cfg1_dog_fixture(oracle):
     want = ((1 - fy)[:, None] * (1 - fx)[None] * g64[y0][:, x0] + (1 - fy)[:, None] * fx[None] * g64[y0][:, x1]
             + fy[:, None] * (1 - fx)[None] * g64[y1][:, x0] + fy[:, None] * fx[None] * g64[y1][:, x1])
     assert np.abs(small[:, :, 0] - want).max() < 1e-4
+
+
+# ── §8(f)#1: the other arms of resize_fast_u8_aa ──────────────────────────────
+def test_pyrdown_2x_matches_the_rounded_box_mean(oracle):
+    """resize/kernels.rs:64-75: (a+b+c+d+2)>>2 — restated independently with numpy integer arithmetic."""
+    rng = np.random.default_rng(5)
+    for (w, h) in [(2, 2), (6, 4), (34, 10), (130, 6)]:
+        src = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        s = src.astype(np.uint16)
+        want = ((s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+        np.testing.assert_array_equal(oracle.resize_fast_u8(src, w // 2, h // 2, 1), want)
+
+
+def test_pyrup_2x_reference_properties(oracle):
+    """resize/mod.rs:597-645 `resize_fast_2x_upscale`: same sizes and generator; corner pixels are preserved exactly.
+    Plus: a constant image stays constant, the horizontal stage of a hand-worked row, and every output is within 2 LSB
+    of the real-valued half-pixel bilinear value (four rounding half-adds, resize/kernels.rs:168-181, :274-281)."""
+    for (w, h) in [(2, 2), (3, 4), (17, 9), (32, 5), (33, 6)]:
+        src = (np.arange(w * h * 3) % 251).astype(np.uint8).reshape(h, w, 3)
+        dst = oracle.resize_fast_u8(src, 2 * w, 2 * h, 1)
+        for (dy, dx, sy, sx) in [(0, 0, 0, 0), (0, 2 * w - 1, 0, w - 1), (2 * h - 1, 0, h - 1, 0), (2 * h - 1, 2 * w - 1, h - 1, w - 1)]:
+            np.testing.assert_array_equal(dst[dy, dx], src[sy, sx])
+        # real-valued reference: half-pixel bilinear with edge clamp
+        ys = np.clip((np.arange(2 * h) + 0.5) * 0.5 - 0.5, 0, h - 1); xs = np.clip((np.arange(2 * w) + 0.5) * 0.5 - 0.5, 0, w - 1)
+        y0 = np.floor(ys).astype(int); x0 = np.floor(xs).astype(int)
+        y1 = np.minimum(y0 + 1, h - 1); x1 = np.minimum(x0 + 1, w - 1)
+        fy = (ys - y0)[:, None, None]; fx = (xs - x0)[None, :, None]
+        f = src.astype(np.float64)
+        ref = (f[y0][:, x0] * (1 - fx) + f[y0][:, x1] * fx) * (1 - fy) + (f[y1][:, x0] * (1 - fx) + f[y1][:, x1] * fx) * fy
+        assert np.abs(dst.astype(np.float64) - ref).max() < 2.0   # four round-half-up half-adds, each off by < 0.5
+    const = np.full((5, 7, 3), 173, np.uint8)
+    assert (oracle.resize_fast_u8(const, 14, 10, 1) == 173).all()
+    row = np.array([[[0, 0, 0], [100, 100, 100]], [[0, 0, 0], [100, 100, 100]]], np.uint8)   # identical rows: vertical stage is the identity
+    np.testing.assert_array_equal(oracle.resize_fast_u8(row, 4, 4, 1)[0, :, 0], [0, 25, 75, 100])   # avg=50: (0+50+1)>>1, (100+50+1)>>1
+
+
+def test_nearest_u8_index_rule(oracle):
+    """resize/nearest.rs:18-21: clamp(floor((i+0.5)*scale)) in f64 (pixel centre then floor, no -0.5)."""
+    rng = np.random.default_rng(6)
+    for (sw, sh, dw, dh, c) in [(7, 5, 3, 2, 3), (5, 5, 9, 7, 1), (64, 48, 1, 1, 4), (1, 1, 8, 8, 2), (23, 37, 11, 17, 5), (4, 5, 2, 3, 3)]:
+        src = rng.integers(0, 256, (sh, sw, c), dtype=np.uint8)
+        xi = np.clip(np.floor((np.arange(dw) + 0.5) * (sw / dw)).astype(np.int64), 0, sw - 1)
+        yi = np.clip(np.floor((np.arange(dh) + 0.5) * (sh / dh)).astype(np.int64), 0, sh - 1)
+        np.testing.assert_array_equal(oracle.resize_fast_u8(src, dw, dh, 0), src[yi][:, xi])
+
+
+def test_resize_fast_u8_path_selection_errors(oracle):
+    """resize/mod.rs:283-337: Bilinear needs C in {1,3,4} and a source of at least 2x2 (unless an exact-2x RGB arm applies)."""
+    with pytest.raises(ValueError, match="UnsupportedChannelCount"):
+        oracle.resize_fast_u8(np.zeros((4, 4, 2), np.uint8), 3, 3, 1)
+    with pytest.raises(ValueError, match="InvalidImageSize"):
+        oracle.resize_fast_u8(np.zeros((4, 1, 3), np.uint8), 3, 3, 1)
+    assert oracle.resize_fast_u8(np.zeros((4, 4, 2), np.uint8), 3, 3, 0).shape == (3, 3, 2)   # Nearest takes any channel count
+    # generic (non-2x) bilinear still goes to the Q14 arm
+    src = oracle.pattern_u8(13 * 9 * 3).reshape(9, 13, 3)
+    np.testing.assert_array_equal(oracle.resize_fast_u8(src, 7, 5, 1), oracle.resize_bilinear_u8(src, 7, 5))
