@@ -58,6 +58,8 @@ def _declare(l: C.CDLL) -> None:
         "kb200_resize_fast_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, i], i),
         "kb200_warp_affine_f32_c3": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, i], i),
         "kb200_warp_perspective_f32_c3": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, i], i),
+        "kb200_warp_affine_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, fp], i),
+        "kb200_warp_perspective_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, fp], i),
         "kb200_invert_affine_transform": ([fp, fp], None),
         "kb200_invert_homography": ([fp, fp], i),
         "kb200_get_rotation_matrix2d": ([f, f, f, f, fp], None),

@@ -291,6 +291,33 @@ def warp_perspective(src: Image, dst: Image, m: Sequence[float], interpolation: 
     _warp("warp_perspective", "kb200_warp_perspective_f32_c3", src, dst, m, 9, interpolation)
 
 
+def _warp_u8(op: str, fn_name: str, src: Image, dst: Image, m: Sequence[float], nm: int) -> None:
+    dev = _prep(op, src, dst)
+    _expect_dtype(src, torch.uint8, "src"); _expect_dtype(dst, torch.uint8, "dst")
+    c = src.num_channels()
+    if c != dst.num_channels() or c not in (1, 3, 4):
+        raise ImageError.UnsupportedChannelCount(c)
+    if len(m) != nm:
+        raise ValueError(f"{op}: expected {nm} matrix entries, got {len(m)}")
+    n = _same_batch(src, dst)
+    st = getattr(_lib.lib(), fn_name)(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
+                                      src.cols(), src.rows(), dst.cols(), dst.rows(), c, n, _lib.f3(m, nm))
+    if st == _lib.ERR_SINGULAR_MATRIX:
+        raise ImageError.CannotComputeDeterminant()
+    _check(st)
+
+
+def warp_affine_u8(src: Image, dst: Image, m: Sequence[float]) -> None:
+    """warp/affine.rs:373 — bilinear u8 affine warp (Q16 coordinates, Q10 weights), forward 2x3 `m`; bit-exact."""
+    _warp_u8("warp_affine_u8", "kb200_warp_affine_u8", src, dst, m, 6)
+
+
+def warp_perspective_u8(src: Image, dst: Image, m: Sequence[float]) -> None:
+    """warp/perspective.rs:179 — bilinear u8 perspective warp (direct coordinates, Q10 weights), forward 3x3 `m`;
+    a singular matrix raises CannotComputeDeterminant; bit-exact."""
+    _warp_u8("warp_perspective_u8", "kb200_warp_perspective_u8", src, dst, m, 9)
+
+
 # ── filters ──────────────────────────────────────────────────────────────────
 def _filter_prep(op: str, src: Image, dst: Image):
     dev = _prep(op, src, dst)

@@ -67,6 +67,10 @@ def _declare(l: C.CDLL) -> None:
     l.ko_resize_normalize_u8_to_f32_chw_bilinear.argtypes = [vp, sz, sz, vp, sz, sz, vp, vp, i]
     l.ko_resize_bilinear_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz]
     l.ko_resize_fast_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, C.c_int]
+    l.ko_warp_affine_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
+    l.ko_warp_affine_u8.restype = C.c_int
+    l.ko_warp_perspective_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
+    l.ko_warp_perspective_u8.restype = C.c_int
     l.ko_resize_fast_u8.restype = C.c_int
     l.ko_invert_affine_transform.argtypes = [vp, vp]
     l.ko_get_rotation_matrix2d.argtypes = [f, f, f, f, vp]
@@ -209,6 +213,26 @@ def resize_fast_u8(src: np.ndarray, dw: int, dh: int, interp: int = 1) -> np.nda
     rc = lib().ko_resize_fast_u8(_p(src), sw, sh, _p(dst), dw, dh, c, interp)
     if rc != 0:
         raise ValueError({-1: "UnsupportedChannelCount", -2: "InvalidImageSize", -3: "UnsupportedInterpolation"}.get(rc, str(rc)))
+    return dst
+
+
+def warp_affine_u8(src: np.ndarray, dw: int, dh: int, m) -> np.ndarray:
+    """warp/affine.rs:373 — Q16 span walk + Q10 sampler, zero fill outside the valid span."""
+    src = np.ascontiguousarray(src, np.uint8)
+    sh, sw, c = src.shape
+    dst = np.full((dh, dw, c), 0xCD, np.uint8)
+    lib().ko_warp_affine_u8(_p(src), sw, sh, _p(dst), dw, dh, c, _p(_f3(m)))
+    return dst
+
+
+def warp_perspective_u8(src: np.ndarray, dw: int, dh: int, m) -> np.ndarray:
+    """warp/perspective.rs:179 — row classification, direct per-column coordinates, Q10 sampler."""
+    src = np.ascontiguousarray(src, np.uint8)
+    sh, sw, c = src.shape
+    dst = np.full((dh, dw, c), 0xCD, np.uint8)
+    rc = lib().ko_warp_perspective_u8(_p(src), sw, sh, _p(dst), dw, dh, c, _p(_f3(m)))
+    if rc != 0:
+        raise ValueError("CannotComputeDeterminant")
     return dst
 
 

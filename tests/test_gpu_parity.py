@@ -271,6 +271,57 @@ def test_resize_fast_u8_errors(kb, dev):
         kb.imgproc.resize_fast_u8(kb.Image.zeros_cuda(kb.ImageSize(4, 4), 3, torch.uint8, dev), d3, kb.InterpolationMode.Bicubic)
 
 
+AFFINES_U8 = [
+    [1, 0, 0, 0, 1, 0], [-1, 0, 63, 0, 1, 0], [1, 0, 5.5, 0, 1, -3.25], [0.7, 0.0, 3.0, 0.0, 1.3, -2.0], [1.0, 0.2, -4.0, -0.1, 0.95, 6.0],
+    [0.8660254, 0.5, -10.0, -0.5, 0.8660254, 20.0], [0.0, 1.0, 0.0, -1.0, 0.0, 47.0], [1e-9, 1.0, 3.0, 1.0, 0.0, 0.0], [2.5, 0, -30, 0, 2.5, -20],
+]
+PERSP_U8 = [
+    [1.02, 0.03, -5.0, -0.03, 1.01, 2.0, 0.00005, 0.00003, 1.0], [0.9, 0.15, 10.0, -0.1, 1.1, -6.0, 0.0, 0.0, 1.0],
+    [1.03, 0.05, -3.0, -0.02, 0.97, 4.0, 2.0 / (97 * 129), 1.5 / (129 * 97), 1.0], [-1.0, 0.0, 63.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0],
+    [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.02, 0.0, -0.5], [0.7, 0.0, 3.0, 0.0, 1.3, -2.0, 0.0, 0.001, 1.0], [1, 0, 0, 0, 1, 0, 0, 0, 1],
+]
+
+
+@pytest.mark.parametrize("mi", range(len(AFFINES_U8)))
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_warp_affine_u8(kb, oracle, dev, mi, c):
+    """warp_affine_u8 (Q16 span walk + Q10 blend) — bit-exact, batched, source and destination sizes differ."""
+    m = AFFINES_U8[mi]
+    n, sw, sh, dw, dh = 2, 64, 48, 70, 41
+    src = np.stack([oracle.pattern_u8(sw * sh * c, 0x51 + i).reshape(sh, sw, c) for i in range(n)])
+    want = np.stack([oracle.warp_affine_u8(src[i], dw, dh, m) for i in range(n)])
+    d = kb.Image(torch.full((n, dh, dw, c), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.warp_affine_u8(kb.Image(cu(src, dev)), d, m)
+    np.testing.assert_array_equal(d.numpy(), want)
+
+
+@pytest.mark.parametrize("mi", range(len(PERSP_U8)))
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_warp_perspective_u8(kb, oracle, dev, mi, c):
+    m = PERSP_U8[mi]
+    n, sw, sh, dw, dh = 2, 64, 48, 64, 48
+    src = np.stack([oracle.pattern_u8(sw * sh * c, 0x61 + i).reshape(sh, sw, c) for i in range(n)])
+    want = np.stack([oracle.warp_perspective_u8(src[i], dw, dh, m) for i in range(n)])
+    d = kb.Image(torch.full((n, dh, dw, c), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.warp_perspective_u8(kb.Image(cu(src, dev)), d, m)
+    np.testing.assert_array_equal(d.numpy(), want)
+
+
+def test_warp_u8_large_and_errors(kb, oracle, dev):
+    src = oracle.pattern_u8(640 * 360 * 3, 9).reshape(360, 640, 3)
+    H = [1.02, 0.03, -40.0 / 6, -0.03, 1.01, 25.0 / 6, 2.0e-6 * 6, 1.2e-6 * 6, 1.0]
+    d = kb.Image.zeros_cuda(kb.ImageSize(640, 360), 3, torch.uint8, dev)
+    kb.imgproc.warp_perspective_u8(kb.Image(cu(src, dev)), d, H)
+    np.testing.assert_array_equal(d.numpy(), oracle.warp_perspective_u8(src, 640, 360, H))
+    M = kb.imgproc.get_rotation_matrix2d((320.0, 180.0), 30.0, 1.0)
+    kb.imgproc.warp_affine_u8(kb.Image(cu(src, dev)), d, M)
+    np.testing.assert_array_equal(d.numpy(), oracle.warp_affine_u8(src, 640, 360, M))
+    with pytest.raises(kb.ImageError, match="singular|determinant"):
+        kb.imgproc.warp_perspective_u8(kb.Image(cu(src, dev)), d, [1, 2, 3, 2, 4, 6, 0, 0, 1])
+    with pytest.raises(kb.ImageError, match="Unsupported channel count"):
+        kb.imgproc.warp_affine_u8(kb.Image.zeros_cuda(kb.ImageSize(8, 8), 2, torch.uint8, dev), kb.Image.zeros_cuda(kb.ImageSize(8, 8), 2, torch.uint8, dev), [1, 0, 0, 0, 1, 0])
+
+
 # ── warps ────────────────────────────────────────────────────────────────────
 AFFINES = [
     ("identity", [1, 0, 0, 0, 1, 0]),

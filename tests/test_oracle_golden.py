@@ -582,3 +582,67 @@ def test_resize_fast_u8_path_selection_errors(oracle):
     # generic (non-2x) bilinear still goes to the Q14 arm
     src = oracle.pattern_u8(13 * 9 * 3).reshape(9, 13, 3)
     np.testing.assert_array_equal(oracle.resize_fast_u8(src, 7, 5, 1), oracle.resize_bilinear_u8(src, 7, 5))
+
+
+# ── §8(f)#1: u8 warps ─────────────────────────────────────────────────────────
+def test_warp_u8_reference_known_answers(oracle):
+    """warp/perspective.rs:338-358 (edge column of a horizontal flip is sampled, not zero-filled), its affine analogue
+    (warp/affine.rs:471), identity = exact copy, and the set-up of warp/perspective.rs:636-668."""
+    src = np.array([10, 20, 30, 40, 50, 60, 70, 80], np.uint8).reshape(2, 4, 1)
+    want = np.array([40, 30, 20, 10, 80, 70, 60, 50], np.uint8).reshape(2, 4, 1)
+    np.testing.assert_array_equal(oracle.warp_perspective_u8(src, 4, 2, [-1, 0, 3, 0, 1, 0, 0, 0, 1]), want)
+    np.testing.assert_array_equal(oracle.warp_affine_u8(src, 4, 2, [-1, 0, 3, 0, 1, 0]), want)
+    img = oracle.pattern_u8(37 * 23 * 3).reshape(23, 37, 3)
+    np.testing.assert_array_equal(oracle.warp_perspective_u8(img, 37, 23, [1, 0, 0, 0, 1, 0, 0, 0, 1]), img)
+    np.testing.assert_array_equal(oracle.warp_affine_u8(img, 37, 23, [1, 0, 0, 0, 1, 0]), img)
+    h, w = 120, 160
+    data = ((np.arange(w * h * 3, dtype=np.uint64) * 37) & 0xFF).astype(np.uint8).reshape(h, w, 3)
+    out = oracle.warp_perspective_u8(data, w, h, [1.02, 0.03, -5.0, -0.03, 1.01, 2.0, 0.00005, 0.00003, 1.0])
+    assert int(out[h // 2, w // 2].astype(np.uint32).sum()) > 0
+    with pytest.raises(ValueError, match="CannotComputeDeterminant"):
+        oracle.warp_perspective_u8(img, 37, 23, [1, 2, 3, 2, 4, 6, 0, 0, 1])
+
+
+def _persp_u8_numpy(src, dw, dh, m, oracle):
+    """Independent per-pixel restatement in numpy float32 (IEEE, unfused): direct coordinate (warp/kernels.rs:107-122) and
+    the bounds-checked Q10 sampler (warp/common.rs:14-63).  No span logic — every pixel is decided by its own coordinate."""
+    f = np.float32
+    inv = oracle.invert_homography(m).astype(f)
+    sh, sw, c = src.shape
+    y = np.arange(dh, dtype=f)[:, None]; x = np.arange(dw, dtype=f)[None, :]
+    nx = (inv[1] * y + inv[2]) + inv[0] * x
+    ny = (inv[4] * y + inv[5]) + inv[3] * x
+    nd = (inv[7] * y + inv[8]) + inv[6] * x
+    with np.errstate(all="ignore"):
+        inv_nd = f(1.0) / nd
+        xf = nx * inv_nd; yf = ny * inv_nd
+    ok = np.isfinite(xf) & np.isfinite(yf)
+    xi = np.floor(np.where(ok, xf, 0)).astype(np.int64); yi = np.floor(np.where(ok, yf, 0)).astype(np.int64)
+    ok &= (xi >= 0) & (xi < sw) & (yi >= 0) & (yi < sh)
+    xi = np.clip(xi, 0, sw - 1); yi = np.clip(yi, 0, sh - 1)
+    fx = ((xf - xi.astype(f)) * f(1024.0)).astype(f); fy = ((yf - yi.astype(f)) * f(1024.0)).astype(f)
+    fx = np.where(ok, fx, 0).astype(np.int64).astype(np.uint32); fy = np.where(ok, fy, 0).astype(np.int64).astype(np.uint32)
+    xi1 = np.minimum(xi + 1, sw - 1); yi1 = np.minimum(yi + 1, sh - 1)
+    s32 = src.astype(np.uint32)
+    top = s32[yi, xi] * (1024 - fx)[..., None] + s32[yi, xi1] * fx[..., None]
+    bot = s32[yi1, xi] * (1024 - fx)[..., None] + s32[yi1, xi1] * fx[..., None]
+    v = (top * (1024 - fy)[..., None] + bot * fy[..., None] + (1 << 19)) >> 20
+    return np.where(ok[..., None], v, 0).astype(np.uint8)
+
+
+PERSP_U8 = [
+    [1.02, 0.03, -5.0, -0.03, 1.01, 2.0, 0.00005, 0.00003, 1.0],
+    [0.9, 0.15, 10.0, -0.1, 1.1, -6.0, 0.0, 0.0, 1.0],
+    [1.03, 0.05, -3.0, -0.02, 0.97, 4.0, 2.0 / (97 * 129), 1.5 / (129 * 97), 1.0],
+    [-1.0, 0.0, 63.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0],
+    [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.02, 0.0, -0.5],       # denominator changes sign inside the row: per-pixel fallback
+    [0.7, 0.0, 3.0, 0.0, 1.3, -2.0, 0.0, 0.001, 1.0],
+]
+
+
+@pytest.mark.parametrize("m", PERSP_U8)
+def test_warp_perspective_u8_span_logic_equals_per_pixel_decision(oracle, m):
+    """The row classification + analytic span of warp/perspective.rs:214-300 must zero exactly the pixels whose own
+    coordinate is outside — checked against the independent per-pixel numpy restatement."""
+    src = oracle.pattern_u8(64 * 48 * 3, 0x77).reshape(48, 64, 3)
+    np.testing.assert_array_equal(oracle.warp_perspective_u8(src, 64, 48, m), _persp_u8_numpy(src, 64, 48, m, oracle))
