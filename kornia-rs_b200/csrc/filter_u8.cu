@@ -1,0 +1,208 @@
+// filter_u8.cu — u8 blurs: gaussian_blur_u8 / box_blur_u8.
+//
+// Reference: filter/ops.rs:22-29 (blur_u8_path), :59-98 (box_blur_u8), :639-757 (gaussian_blur_u8), :759-770
+// (quantize_kernel_256), :773-851 + :852-1100 (general Q8 two-pass: H pass (acc + 128) >> 8 into a u8 intermediate with
+// the row replicated left/right, V pass likewise over row-clamped H rows), :1105-1285 (k = 3, sigma in [0.6, 1.2]:
+// [1,2,1]/4 as rhadd(rhadd(a,b), rhadd(b,d)) per axis).  Integer arithmetic throughout — bit-exact class.
+//
+// Kernel: one CTA per (image, 32x32-pixel tile).  The tile plus its halo is gathered into shared memory with the
+// replicate rule applied at gather time, the H pass writes its u8 result to a second shared array (the reference's u8
+// intermediate — the rounding between the passes is part of the result), the V pass reads it and stores.  Both the
+// Q8 and the binomial arithmetic run through the same staging.
+#include <algorithm>
+#include <vector>
+
+#include "kb200_common.cuh"
+
+namespace kb200 {
+
+static constexpr int U8B_TW = 32, U8B_TH = 32, U8B_MAXK = 31;
+
+struct U8Taps {
+    uint8_t kx[32], ky[32];
+    int kxn, kyn;
+    int binomial;   // 1: [1,2,1]/4 rounding half-add path (kxn = kyn = 3)
+};
+
+__device__ __forceinline__ uint32_t rhadd_u8(uint32_t a, uint32_t b) { return (a + b + 1u) >> 1; }
+
+// K > 0: both axes have K taps, held in registers (the loops unroll); K == 0: run-time tap counts, taps read from shared
+// memory.  (Indexing the taps in the kernel-parameter bank costs one LDC per tap per byte — measured 5x slower.)
+template <int C, int K>
+__global__ void __launch_bounds__(256) blur_u8_tile_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cols,
+                                                           uint32_t rows, uint32_t tiles_x, uint32_t tiles_y,
+                                                           const __grid_constant__ U8Taps T) {
+    extern __shared__ uint8_t u8b_smem[];
+    __shared__ uint32_t tap_s[2][32];
+    const int kxn = K > 0 ? K : T.kxn, kyn = K > 0 ? K : T.kyn;
+    uint32_t kxr[K > 0 ? K : 1], kyr[K > 0 ? K : 1];
+    if (K > 0) {
+#pragma unroll
+        for (int k = 0; k < (K > 0 ? K : 1); ++k) { kxr[k] = T.kx[k]; kyr[k] = T.ky[k]; }
+    } else if (threadIdx.x < 32) {
+        tap_s[0][threadIdx.x] = T.kx[threadIdx.x]; tap_s[1][threadIdx.x] = T.ky[threadIdx.x];
+    }
+    const int hx = kxn / 2, hy = kyn / 2;
+    const int in_wpx = U8B_TW + 2 * hx, in_h = U8B_TH + 2 * hy;
+    const int in_wb = in_wpx * C, mid_wb = U8B_TW * C;
+    uint8_t* in = u8b_smem;                       // [in_h][in_wb]
+    uint8_t* mid = u8b_smem + (size_t)in_h * in_wb;   // [in_h][mid_wb]
+    const uint32_t t = blockIdx.x;
+    const uint32_t img = t / (tiles_x * tiles_y), tt = t - img * tiles_x * tiles_y;
+    const int x0 = (int)(tt % tiles_x) * U8B_TW, y0 = (int)(tt / tiles_x) * U8B_TH;
+    const uint8_t* s = src + (size_t)img * cols * rows * C;
+    uint8_t* d = dst + (size_t)img * cols * rows * C;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8: rows by ty, bytes / pixels by tx — no index divisions
+    // gather with the replicate rule (clamped row / column indices)
+    for (int r = ty; r < in_h; r += 8) {
+        const int sy = min(max(y0 - hy + r, 0), (int)rows - 1);
+        const uint8_t* srow = s + (size_t)sy * cols * C;
+        for (int p = tx; p < in_wpx; p += 32) {
+            const int sx = min(max(x0 - hx + p, 0), (int)cols - 1);
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) in[r * in_wb + p * C + ch] = srow[sx * C + ch];
+        }
+    }
+    __syncthreads();
+    // H pass -> u8 intermediate
+    for (int r = ty; r < in_h; r += 8) {
+        for (int j = tx; j < mid_wb; j += 32) {
+            const uint8_t* ip = in + r * in_wb + j;          // tap k at ip[k*C]
+            uint32_t v;
+            if (T.binomial) v = rhadd_u8(rhadd_u8(ip[0], ip[C]), rhadd_u8(ip[C], ip[2 * C]));
+            else {
+                uint32_t acc = 0;
+                if (K > 0) {
+#pragma unroll
+                    for (int k = 0; k < (K > 0 ? K : 1); ++k) acc += (uint32_t)ip[k * C] * kxr[k];
+                } else {
+                    for (int k = 0; k < kxn; ++k) acc += (uint32_t)ip[k * C] * tap_s[0][k];
+                }
+                v = (acc + 128u) >> 8;
+            }
+            mid[r * mid_wb + j] = (uint8_t)v;
+        }
+    }
+    __syncthreads();
+    // V pass -> global
+    for (int r = ty; r < U8B_TH; r += 8) {
+        const int gy = y0 + r;
+        if (gy >= (int)rows) break;
+        uint8_t* drow = d + (size_t)gy * cols * C + (size_t)x0 * C;
+        const int nb = min(mid_wb, ((int)cols - x0) * C);
+        for (int j = tx; j < nb; j += 32) {
+            const uint8_t* mp = mid + r * mid_wb + j;        // tap k at mp[k*mid_wb]
+            uint32_t v;
+            if (T.binomial) v = rhadd_u8(rhadd_u8(mp[0], mp[mid_wb]), rhadd_u8(mp[mid_wb], mp[2 * mid_wb]));
+            else {
+                uint32_t acc = 0;
+                if (K > 0) {
+#pragma unroll
+                    for (int k = 0; k < (K > 0 ? K : 1); ++k) acc += (uint32_t)mp[k * mid_wb] * kyr[k];
+                } else {
+                    for (int k = 0; k < kyn; ++k) acc += (uint32_t)mp[k * mid_wb] * tap_s[1][k];
+                }
+                v = (acc + 128u) >> 8;
+            }
+            drow[j] = (uint8_t)v;
+        }
+    }
+}
+
+// filter/ops.rs:759-770
+static void quantize_kernel_256(const float* k, int n, uint8_t* out) {
+    uint32_t sum = 0;
+    for (int i = 0; i < n; ++i) {
+        const float v = k[i] * 256.0f + 0.5f;
+        out[i] = (v != v || v <= 0.0f) ? 0 : (v >= 255.0f ? 255 : (uint8_t)v);   // `as u8`: saturating, NaN -> 0
+        sum += out[i];
+    }
+    if (sum != 256) {
+        const int c = (int)out[n / 2] + (256 - (int)sum);
+        out[n / 2] = (uint8_t)std::min(std::max(c, 0), 255);
+    }
+}
+
+static int launch_blur_u8(cudaStream_t s, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len, uint32_t cols, uint32_t rows,
+                          uint32_t C, uint32_t batch, const U8Taps& T) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_geometry(cols, rows, cols, rows, batch));
+    if (!(C == 1 || C == 3 || C == 4)) return fail(KB200_ERR_UNSUPPORTED, "u8 blur supports 1, 3 or 4 channels, got %u", C);
+    const size_t n = (size_t)cols * rows * C * batch;
+    KB200_TRY(check_slice("src", src_len, n)); KB200_TRY(check_slice("dst", dst_len, n));
+    if (src == dst) return fail(KB200_ERR_INVALID_ARGUMENT, "src and dst must not alias (tiles read a halo)");
+    if ((size_t)cols * C > 0x7FFFFFFFull || rows > 0x7FFFFFFFu) return fail(KB200_ERR_DIMS_TOO_LARGE, "u8 blur image dimensions too large");
+    const uint32_t tiles_x = div_up(cols, U8B_TW), tiles_y = div_up(rows, U8B_TH);
+    const size_t ntiles = (size_t)tiles_x * tiles_y * batch;
+    if (ntiles > 0x7FFFFFFFull) return fail(KB200_ERR_DIMS_TOO_LARGE, "too many tiles (%zu)", ntiles);
+    const int hx = T.kxn / 2, hy = T.kyn / 2;
+    const size_t smem = (size_t)(U8B_TH + 2 * hy) * ((U8B_TW + 2 * hx) * C + U8B_TW * C);
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
+        }
+        kern<<<(unsigned)ntiles, 256, smem, s>>>(src, dst, cols, rows, tiles_x, tiles_y, T);
+        return check_launch("blur_u8_tile_kernel");
+    };
+#define KB200_U8B(CC)                                                                   \
+    if (C == CC) {                                                                      \
+        if (T.kxn == T.kyn && T.kxn == 3) return go(blur_u8_tile_kernel<CC, 3>);        \
+        if (T.kxn == T.kyn && T.kxn == 5) return go(blur_u8_tile_kernel<CC, 5>);        \
+        if (T.kxn == T.kyn && T.kxn == 7) return go(blur_u8_tile_kernel<CC, 7>);        \
+        return go(blur_u8_tile_kernel<CC, 0>);                                          \
+    }
+    KB200_U8B(1) KB200_U8B(3) KB200_U8B(4)
+#undef KB200_U8B
+    return KB200_OK;
+}
+
+}  // namespace kb200
+
+using namespace kb200;
+
+extern "C" {
+
+KB200_API void kb200_quantize_kernel_256(const float* kernel, uint32_t n, uint8_t* out) {
+    if (kernel && out && n) quantize_kernel_256(kernel, (int)n, out);
+}
+
+KB200_API int kb200_gaussian_blur_u8(kb200_stream_t stream, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len, uint32_t cols,
+                                     uint32_t rows, uint32_t channels, uint32_t batch, uint32_t ksize_x, uint32_t ksize_y, float sigma_x,
+                                     float sigma_y) {
+    uint32_t kxn, kyn;
+    float sx, sy;
+    KB200_TRY(kb200_gaussian_resolve(ksize_x, ksize_y, sigma_x, sigma_y, &kxn, &kyn, &sx, &sy));   // InvalidSigmaValue
+    if (kxn > (uint32_t)U8B_MAXK || kyn > (uint32_t)U8B_MAXK)
+        return fail(KB200_ERR_UNSUPPORTED, "gaussian_blur_u8 supports up to %d taps per axis, got (%u, %u)", U8B_MAXK, kxn, kyn);
+    U8Taps T{};
+    T.kxn = (int)kxn; T.kyn = (int)kyn;
+    // blur_u8_path (filter/ops.rs:22-29)
+    T.binomial = (kxn == 3 && kyn == 3 && sx >= 0.6f && sx <= 1.2f && sy >= 0.6f && sy <= 1.2f) ? 1 : 0;
+    if (!T.binomial) {
+        float fx[32], fy[32];
+        kb200_gaussian_kernel_1d(kxn, sx, fx);
+        kb200_gaussian_kernel_1d(kyn, sy, fy);
+        quantize_kernel_256(fx, (int)kxn, T.kx);
+        quantize_kernel_256(fy, (int)kyn, T.ky);
+    }
+    return launch_blur_u8(as_stream(stream), src, src_len, dst, dst_len, cols, rows, channels, batch, T);
+}
+
+KB200_API int kb200_box_blur_u8(kb200_stream_t stream, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len, uint32_t cols,
+                                uint32_t rows, uint32_t channels, uint32_t batch, uint32_t ksize_x, uint32_t ksize_y) {
+    if (ksize_x == 0 || ksize_y == 0 || ksize_x % 2 == 0 || ksize_y % 2 == 0)   // filter/ops.rs:74-76: InvalidSigmaValue(kx, ky)
+        return fail(KB200_ERR_INVALID_KERNEL, "Invalid sigma value: (%g, %g)", (double)ksize_x, (double)ksize_y);
+    if (ksize_x > (uint32_t)U8B_MAXK || ksize_y > (uint32_t)U8B_MAXK)
+        return fail(KB200_ERR_UNSUPPORTED, "box_blur_u8 supports up to %d taps per axis, got (%u, %u)", U8B_MAXK, ksize_x, ksize_y);
+    U8Taps T{};
+    T.kxn = (int)ksize_x; T.kyn = (int)ksize_y; T.binomial = 0;
+    float fx[32], fy[32];
+    for (uint32_t i = 0; i < ksize_x; ++i) fx[i] = 1.0f / (float)ksize_x;   // filter/kernels.rs:10-13
+    for (uint32_t i = 0; i < ksize_y; ++i) fy[i] = 1.0f / (float)ksize_y;
+    quantize_kernel_256(fx, (int)ksize_x, T.kx);
+    quantize_kernel_256(fy, (int)ksize_y, T.ky);
+    return launch_blur_u8(as_stream(stream), src, src_len, dst, dst_len, cols, rows, channels, batch, T);
+}
+
+}  // extern "C"

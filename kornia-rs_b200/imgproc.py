@@ -327,6 +327,38 @@ def _filter_prep(op: str, src: Image, dst: Image):
     return dev, _same_batch(src, dst)
 
 
+def _blur_u8_prep(op: str, src: Image, dst: Image):
+    dev = _prep(op, src, dst)
+    _expect_dtype(src, torch.uint8, "src"); _expect_dtype(dst, torch.uint8, "dst")
+    if src.size() != dst.size() or src.num_channels() != dst.num_channels():
+        raise ImageError.InvalidImageSize(src.cols(), src.rows(), dst.cols(), dst.rows())   # filter/ops.rs:645-652
+    if src.num_channels() not in (1, 3, 4):
+        raise ImageError.UnsupportedChannelCount(src.num_channels())
+    return dev, _same_batch(src, dst)
+
+
+def gaussian_blur_u8(src: Image, dst: Image, kernel_size: tuple[int, int], sigma: tuple[float, float]) -> None:
+    """filter/ops.rs:639 — u8 gaussian blur, replicate border: Q8 two-pass with a u8 intermediate, or the [1,2,1]/4
+    rounding-half-add path for k = 3 with sigma in [0.6, 1.2] (`blur_u8_path`).  Bit-exact."""
+    dev, n = _blur_u8_prep("gaussian_blur_u8", src, dst)
+    st = _lib.lib().kb200_gaussian_blur_u8(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), src.cols(),
+                                           src.rows(), src.num_channels(), n, int(kernel_size[0]), int(kernel_size[1]),
+                                           float(sigma[0]), float(sigma[1]))
+    if st == _lib.ERR_INVALID_KERNEL:
+        raise ImageError.InvalidSigmaValue(float(sigma[0]), float(sigma[1]))
+    _check(st)
+
+
+def box_blur_u8(src: Image, dst: Image, kernel_size: tuple[int, int]) -> None:
+    """filter/ops.rs:59 — u8 box blur through the same Q8 two-pass; kernel sizes must be odd and positive."""
+    dev, n = _blur_u8_prep("box_blur_u8", src, dst)
+    kx, ky = int(kernel_size[0]), int(kernel_size[1])
+    if kx <= 0 or ky <= 0 or kx % 2 == 0 or ky % 2 == 0:
+        raise ImageError.InvalidSigmaValue(float(kx), float(ky))
+    _check(_lib.lib().kb200_box_blur_u8(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), src.cols(),
+                                        src.rows(), src.num_channels(), n, kx, ky))
+
+
 def separable_filter(src: Image, dst: Image, kernel_x: Sequence[float], kernel_y: Sequence[float]) -> None:
     """filter/separable_filter.rs:166 — correlation, zero border, H then V; one fused kernel here."""
     if len(kernel_x) == 0 or len(kernel_y) == 0:

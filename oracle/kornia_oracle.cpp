@@ -933,6 +933,95 @@ KO_API int ko_gaussian_blur_f32(const float* src, float* dst, size_t rows, size_
     return 0;
 }
 
+// ─────────────────────────────────────────────────────────────────────────────
+// §8(f)#1 — u8 blurs: filter/ops.rs:22-29 (path selection), :59-98 (box_blur_u8), :639-757 (gaussian_blur_u8),
+// :759-770 (quantize_kernel_256), :773-851 + :852-1100 (general Q8 two-pass, replicate border, u8 intermediate),
+// :1105-1285 ([1,2,1]/4 binomial path as nested rounding half-adds).
+// ─────────────────────────────────────────────────────────────────────────────
+// (k * 256 + 0.5) as u8 per tap (saturating), then the centre tap absorbs the rounding so the weights sum to 256
+KO_API void ko_quantize_kernel_256(const float* k, size_t n, uint8_t* out) {
+    uint32_t sum = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const float v = k[i] * 256.0f + 0.5f;
+        out[i] = std::isnan(v) || v <= 0.0f ? 0 : (v >= 255.0f ? 255 : (uint8_t)v);
+        sum += out[i];
+    }
+    if (sum != 256) {
+        int c = (int)out[n / 2] + (256 - (int)(uint16_t)sum);   // i16 arithmetic in the reference; sums stay far below 2^15
+        out[n / 2] = (uint8_t)std::min(std::max(c, 0), 255);
+    }
+}
+
+static inline size_t clampi(long long v, size_t n) { return (size_t)std::min<long long>(std::max<long long>(v, 0), (long long)n - 1); }
+
+// General Q8 path: H pass (acc + 128) >> 8 to u8 with the row replicated left/right, V pass likewise over
+// row-clamped H rows.
+static void separable_blur_u8(const uint8_t* src, uint8_t* dst, size_t rows, size_t cols, size_t C, const uint8_t* kx, size_t kxn,
+                              const uint8_t* ky, size_t kyn) {
+    const size_t stride = cols * C, hx = kxn / 2, hy = kyn / 2;
+    std::vector<uint8_t> h(rows * stride);
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t x = 0; x < cols; ++x)
+            for (size_t ch = 0; ch < C; ++ch) {
+                uint32_t acc = 0;
+                for (size_t k = 0; k < kxn; ++k) acc += (uint32_t)src[r * stride + clampi((long long)x + (long long)k - (long long)hx, cols) * C + ch] * kx[k];
+                h[r * stride + x * C + ch] = (uint8_t)((acc + 128) >> 8);
+            }
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t j = 0; j < stride; ++j) {
+            uint32_t acc = 0;
+            for (size_t k = 0; k < kyn; ++k) acc += (uint32_t)h[clampi((long long)r + (long long)k - (long long)hy, rows) * stride + j] * ky[k];
+            dst[r * stride + j] = (uint8_t)((acc + 128) >> 8);
+        }
+}
+
+static inline uint32_t rhadd(uint32_t a, uint32_t b) { return (a + b + 1) >> 1; }
+// [1,2,1]/4 as rhadd(rhadd(a,b), rhadd(b,d)), horizontally then vertically, neighbours replicated at the borders
+static void binomial3_u8(const uint8_t* src, uint8_t* dst, size_t rows, size_t cols, size_t C) {
+    const size_t stride = cols * C;
+    std::vector<uint8_t> h(rows * stride);
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t x = 0; x < cols; ++x)
+            for (size_t ch = 0; ch < C; ++ch) {
+                const uint32_t a = src[r * stride + clampi((long long)x - 1, cols) * C + ch], b = src[r * stride + x * C + ch],
+                               d = src[r * stride + clampi((long long)x + 1, cols) * C + ch];
+                h[r * stride + x * C + ch] = (uint8_t)rhadd(rhadd(a, b), rhadd(b, d));
+            }
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t j = 0; j < stride; ++j) {
+            const uint32_t a = h[clampi((long long)r - 1, rows) * stride + j], b = h[r * stride + j], d = h[clampi((long long)r + 1, rows) * stride + j];
+            dst[r * stride + j] = (uint8_t)rhadd(rhadd(a, b), rhadd(b, d));
+        }
+}
+
+// returns 0, -1 (InvalidSigmaValue)
+KO_API int ko_gaussian_blur_u8(const uint8_t* src, uint8_t* dst, size_t rows, size_t cols, size_t C, size_t kx_in, size_t ky_in,
+                               float sx_in, float sy_in) {
+    size_t kxn, kyn;
+    float sx, sy;
+    if (ko_gaussian_resolve(kx_in, ky_in, sx_in, sy_in, &kxn, &kyn, &sx, &sy) != 0) return -1;
+    if (kxn == 3 && kyn == 3 && sx >= 0.6f && sx <= 1.2f && sy >= 0.6f && sy <= 1.2f) { binomial3_u8(src, dst, rows, cols, C); return 0; }  // blur_u8_path
+    std::vector<float> fx(kxn), fy(kyn);
+    ko_gaussian_kernel_1d(kxn, sx, fx.data());
+    ko_gaussian_kernel_1d(kyn, sy, fy.data());
+    std::vector<uint8_t> ikx(kxn), iky(kyn);
+    ko_quantize_kernel_256(fx.data(), kxn, ikx.data());
+    ko_quantize_kernel_256(fy.data(), kyn, iky.data());
+    separable_blur_u8(src, dst, rows, cols, C, ikx.data(), kxn, iky.data(), kyn);
+    return 0;
+}
+
+// returns 0, -1 (InvalidSigmaValue: zero or even kernel size)
+KO_API int ko_box_blur_u8(const uint8_t* src, uint8_t* dst, size_t rows, size_t cols, size_t C, size_t kx, size_t ky) {
+    if (kx == 0 || ky == 0 || kx % 2 == 0 || ky % 2 == 0) return -1;
+    std::vector<float> fx(kx, 1.0f / (float)kx), fy(ky, 1.0f / (float)ky);   // filter/kernels.rs:10-13
+    std::vector<uint8_t> ikx(kx), iky(ky);
+    ko_quantize_kernel_256(fx.data(), kx, ikx.data());
+    ko_quantize_kernel_256(fy.data(), ky, iky.data());
+    separable_blur_u8(src, dst, rows, cols, C, ikx.data(), kx, iky.data(), ky);
+    return 0;
+}
+
 KO_API int ko_sobel_f32(const float* src, float* dst, size_t rows, size_t cols, size_t C, size_t ksize, int mt) {
     float kx[5], ky[5];
     if (ko_sobel_kernel_1d(ksize, kx, ky) != 0) return -1;

@@ -67,6 +67,11 @@ def _declare(l: C.CDLL) -> None:
     l.ko_resize_normalize_u8_to_f32_chw_bilinear.argtypes = [vp, sz, sz, vp, sz, sz, vp, vp, i]
     l.ko_resize_bilinear_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz]
     l.ko_resize_fast_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, C.c_int]
+    l.ko_quantize_kernel_256.argtypes = [vp, sz, vp]
+    l.ko_gaussian_blur_u8.argtypes = [vp, vp, sz, sz, sz, sz, sz, f, f]
+    l.ko_gaussian_blur_u8.restype = C.c_int
+    l.ko_box_blur_u8.argtypes = [vp, vp, sz, sz, sz, sz, sz]
+    l.ko_box_blur_u8.restype = C.c_int
     l.ko_warp_affine_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
     l.ko_warp_affine_u8.restype = C.c_int
     l.ko_warp_perspective_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
@@ -457,3 +462,31 @@ def preprocess_cpu_rgb_bilinear(src: np.ndarray, dw: int, dh: int, mode: int, me
 
 def count_touched_resize(sw: int, sh: int, dw: int, dh: int, kind: int) -> int:
     return int(lib().ko_count_touched_resize(sw, sh, dw, dh, kind))
+
+
+# ── u8 blurs ───────────────────────────────────────────────
+def quantize_kernel_256(k) -> np.ndarray:
+    k = _f3(k)
+    out = np.zeros(len(k), np.uint8)
+    lib().ko_quantize_kernel_256(_p(k), len(k), _p(out))
+    return out
+
+
+def gaussian_blur_u8(src: np.ndarray, ksize=(0, 0), sigma=(0.0, 0.0)) -> np.ndarray:
+    """filter/ops.rs:639 — Q8 two-pass (or the [1,2,1]/4 binomial path for k=3, sigma in [0.6, 1.2]), replicate border."""
+    src = np.ascontiguousarray(src, np.uint8)
+    rows, cols, c = src.shape
+    dst = np.zeros_like(src)
+    if lib().ko_gaussian_blur_u8(_p(src), _p(dst), rows, cols, c, ksize[0], ksize[1], sigma[0], sigma[1]) != 0:
+        raise ValueError("InvalidSigmaValue")
+    return dst
+
+
+def box_blur_u8(src: np.ndarray, ksize) -> np.ndarray:
+    """filter/ops.rs:59 — uniform Q8 kernel through the same two-pass path."""
+    src = np.ascontiguousarray(src, np.uint8)
+    rows, cols, c = src.shape
+    dst = np.zeros_like(src)
+    if lib().ko_box_blur_u8(_p(src), _p(dst), rows, cols, c, ksize[0], ksize[1]) != 0:
+        raise ValueError("InvalidSigmaValue")
+    return dst

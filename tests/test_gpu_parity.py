@@ -322,6 +322,45 @@ def test_warp_u8_large_and_errors(kb, oracle, dev):
         kb.imgproc.warp_affine_u8(kb.Image.zeros_cuda(kb.ImageSize(8, 8), 2, torch.uint8, dev), kb.Image.zeros_cuda(kb.ImageSize(8, 8), 2, torch.uint8, dev), [1, 0, 0, 0, 1, 0])
 
 
+U8_BLURS = [  # (rows, cols, c, kx, ky, sx, sy)
+    (37, 83, 1, 5, 5, 1.0, 1.0), (37, 83, 1, 7, 7, 2.0, 2.0), (17, 45, 3, 3, 3, 1.0, 1.0), (23, 31, 3, 5, 3, 1.5, 2.0), (23, 31, 4, 9, 9, 0.0, 0.0),
+    (9, 11, 3, 3, 3, 2.0, 2.0), (70, 65, 3, 0, 0, 0.8, 0.0), (33, 64, 3, 31, 31, 4.0, 4.0), (5, 1, 1, 3, 3, 1.0, 1.0), (1, 5, 1, 3, 3, 1.0, 1.0),
+    (100, 130, 3, 5, 5, 1.5, 1.5), (2, 2, 4, 7, 7, 1.0, 1.0),
+]
+
+
+@pytest.mark.parametrize("rows,cols,c,kx,ky,sx,sy", U8_BLURS)
+def test_gaussian_blur_u8(kb, oracle, dev, rows, cols, c, kx, ky, sx, sy):
+    n = 2
+    src = np.stack([oracle.pattern_u8(rows * cols * c, 0x71 + i).reshape(rows, cols, c) for i in range(n)])
+    want = np.stack([oracle.gaussian_blur_u8(src[i], (kx, ky), (sx, sy)) for i in range(n)])
+    d = kb.Image(torch.full((n, rows, cols, c), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.gaussian_blur_u8(kb.Image(cu(src, dev)), d, (kx, ky), (sx, sy))
+    np.testing.assert_array_equal(d.numpy(), want)
+
+
+@pytest.mark.parametrize("kx,ky", [(3, 3), (5, 5), (7, 3), (1, 9), (15, 15)])
+def test_box_blur_u8(kb, oracle, dev, kx, ky):
+    src = oracle.pattern_u8(41 * 67 * 3, 0x81).reshape(41, 67, 3)
+    d = kb.Image.zeros_cuda(kb.ImageSize(67, 41), 3, torch.uint8, dev)
+    kb.imgproc.box_blur_u8(kb.Image(cu(src, dev)), d, (kx, ky))
+    np.testing.assert_array_equal(d.numpy(), oracle.box_blur_u8(src, (kx, ky)))
+
+
+def test_blur_u8_errors_and_4k(kb, oracle, dev):
+    s3 = kb.Image.zeros_cuda(kb.ImageSize(8, 8), 3, torch.uint8, dev)
+    with pytest.raises(kb.ImageError, match="Invalid sigma"):
+        kb.imgproc.box_blur_u8(s3, kb.Image.zeros_cuda(kb.ImageSize(8, 8), 3, torch.uint8, dev), (4, 3))
+    with pytest.raises(kb.ImageError, match="Invalid sigma"):
+        kb.imgproc.gaussian_blur_u8(s3, kb.Image.zeros_cuda(kb.ImageSize(8, 8), 3, torch.uint8, dev), (4, 4), (1.0, 1.0))
+    with pytest.raises(kb.ImageError, match="Invalid image size"):
+        kb.imgproc.gaussian_blur_u8(s3, kb.Image.zeros_cuda(kb.ImageSize(9, 8), 3, torch.uint8, dev), (3, 3), (1.0, 1.0))
+    src = oracle.pattern_u8(1920 * 270 * 3, 3).reshape(270, 1920, 3)
+    d = kb.Image.zeros_cuda(kb.ImageSize(1920, 270), 3, torch.uint8, dev)
+    kb.imgproc.gaussian_blur_u8(kb.Image(cu(src, dev)), d, (5, 5), (1.5, 1.5))
+    np.testing.assert_array_equal(d.numpy(), oracle.gaussian_blur_u8(src, (5, 5), (1.5, 1.5)))
+
+
 # ── warps ────────────────────────────────────────────────────────────────────
 AFFINES = [
     ("identity", [1, 0, 0, 0, 1, 0]),

@@ -646,3 +646,82 @@ def test_warp_perspective_u8_span_logic_equals_per_pixel_decision(oracle, m):
     coordinate is outside — checked against the independent per-pixel numpy restatement."""
     src = oracle.pattern_u8(64 * 48 * 3, 0x77).reshape(48, 64, 3)
     np.testing.assert_array_equal(oracle.warp_perspective_u8(src, 64, 48, m), _persp_u8_numpy(src, 64, 48, m, oracle))
+
+
+# ── §8(f)#1: u8 blurs ─────────────────────────────────────────────────────────
+def _knuth_u8(n):
+    """the reference tests' generator: ((i * 2654435761) >> 24) as u8 with usize wrapping (filter/ops.rs:1992-1994)"""
+    i = np.arange(n, dtype=np.uint64)
+    return (((i * np.uint64(2654435761)) & np.uint64(0xFFFFFFFFFFFFFFFF)) >> np.uint64(24)).astype(np.uint8)
+
+
+def _q8_two_pass_numpy(src, ikx, iky):
+    """Independent numpy restatement of the general path: replicate border, (acc+128)>>8 after EACH pass."""
+    rows, cols, c = src.shape
+    hx, hy = len(ikx) // 2, len(iky) // 2
+    p = np.pad(src.astype(np.uint32), ((0, 0), (hx, hx), (0, 0)), mode="edge")
+    h = sum(p[:, k:k + cols] * np.uint32(ikx[k]) for k in range(len(ikx)))
+    h = ((h + 128) >> 8).astype(np.uint32)
+    p = np.pad(h, ((hy, hy), (0, 0), (0, 0)), mode="edge")
+    v = sum(p[k:k + rows] * np.uint32(iky[k]) for k in range(len(iky)))
+    return ((v + 128) >> 8).astype(np.uint8)
+
+
+def test_quantize_kernel_256(oracle):
+    """filter/ops.rs:759-770: (k*256 + 0.5) as u8, centre tap absorbs the rounding so the sum is exactly 256."""
+    np.testing.assert_array_equal(oracle.quantize_kernel_256([0.0625, 0.25, 0.375, 0.25, 0.0625]), [16, 64, 96, 64, 16])
+    for k in (3, 5, 7, 9, 15, 31):
+        assert int(oracle.quantize_kernel_256(np.full(k, 1.0 / k, np.float32)).astype(np.uint32).sum()) == 256
+    for (k, sg) in [(3, 0.85), (5, 1.0), (5, 1.5), (7, 2.0), (9, 1.0), (31, 4.0)]:
+        q = oracle.quantize_kernel_256(oracle.gaussian_kernel_1d(k, sg))
+        assert int(q.astype(np.uint32).sum()) == 256 and (q == q[::-1]).all()
+
+
+def test_gaussian_blur_u8_general_path(oracle):
+    """filter/ops.rs:2020-2061 (5x5 goes to the general Q8 path) on the reference's 37x83 generator image, plus other
+    kernel sizes / channel counts, against the independent numpy two-pass."""
+    src = _knuth_u8(37 * 83).reshape(37, 83, 1)
+    ik = oracle.quantize_kernel_256(oracle.gaussian_kernel_1d(5, 1.0))
+    np.testing.assert_array_equal(oracle.gaussian_blur_u8(src, (5, 5), (1.0, 1.0)), _q8_two_pass_numpy(src, ik, ik))
+    for (kx, ky, sx, sy, c) in [(7, 7, 2.0, 2.0, 1), (5, 3, 1.5, 2.0, 3), (9, 9, 0.0, 0.0, 4), (3, 3, 2.0, 2.0, 3), (0, 0, 0.8, 0.0, 3)]:
+        img = _knuth_u8(23 * 31 * c).reshape(23, 31, c)
+        kxn, kyn, rsx, rsy = oracle.gaussian_resolve(kx, ky, sx, sy)
+        ikx = oracle.quantize_kernel_256(oracle.gaussian_kernel_1d(kxn, rsx)); iky = oracle.quantize_kernel_256(oracle.gaussian_kernel_1d(kyn, rsy))
+        np.testing.assert_array_equal(oracle.gaussian_blur_u8(img, (kx, ky), (sx, sy)), _q8_two_pass_numpy(img, ikx, iky))
+
+
+def test_gaussian_blur_u8_binomial_path(oracle):
+    """k = 3, sigma in [0.6, 1.2] takes the [1,2,1]/4 half-add path (filter/ops.rs:22-29); it stays within 2 LSB of the
+    general Q8 path at sigma 0.85 (filter/ops.rs:2063-2104), and 1-column / 1-row images work (:2107-2156)."""
+    for (rows, cols, c) in [(37, 83, 1), (17, 45, 3)]:
+        src = _knuth_u8(rows * cols * c).reshape(rows, cols, c)
+        binom = oracle.gaussian_blur_u8(src, (3, 3), (1.0, 1.0))
+        ik = oracle.quantize_kernel_256(oracle.gaussian_kernel_1d(3, 0.85))
+        gen = _q8_two_pass_numpy(src, ik, ik)
+        assert int(np.abs(binom.astype(np.int16) - gen.astype(np.int16)).max()) <= 2
+        # independent restatement of the half-add form
+        s = src.astype(np.uint32)
+        rh = lambda a, b: (a + b + 1) >> 1
+        p = np.pad(s, ((0, 0), (1, 1), (0, 0)), mode="edge")
+        h = rh(rh(p[:, :-2], p[:, 1:-1]), rh(p[:, 1:-1], p[:, 2:]))
+        p = np.pad(h, ((1, 1), (0, 0), (0, 0)), mode="edge")
+        np.testing.assert_array_equal(binom, rh(rh(p[:-2], p[1:-1]), rh(p[1:-1], p[2:])).astype(np.uint8))
+    col = (np.arange(5) * 50).astype(np.uint8).reshape(5, 1, 1)
+    assert oracle.gaussian_blur_u8(col, (3, 3), (1.0, 1.0)).shape == (5, 1, 1)
+    assert oracle.gaussian_blur_u8(col.reshape(1, 5, 1), (3, 3), (1.0, 1.0)).shape == (1, 5, 1)
+    # sigma outside [0.6, 1.2] -> general path even for k = 3
+    src = _knuth_u8(9 * 11 * 3).reshape(9, 11, 3)
+    ik = oracle.quantize_kernel_256(oracle.gaussian_kernel_1d(3, 2.0))
+    np.testing.assert_array_equal(oracle.gaussian_blur_u8(src, (3, 3), (2.0, 2.0)), _q8_two_pass_numpy(src, ik, ik))
+
+
+def test_box_blur_u8(oracle):
+    src = _knuth_u8(19 * 27 * 3).reshape(19, 27, 3)
+    for (kx, ky) in [(3, 3), (5, 5), (7, 3), (1, 9)]:
+        ikx = oracle.quantize_kernel_256(np.full(kx, 1.0 / kx, np.float32)); iky = oracle.quantize_kernel_256(np.full(ky, 1.0 / ky, np.float32))
+        np.testing.assert_array_equal(oracle.box_blur_u8(src, (kx, ky)), _q8_two_pass_numpy(src, ikx, iky))
+    for bad in [(0, 3), (4, 3), (3, 2)]:
+        with pytest.raises(ValueError, match="InvalidSigmaValue"):
+            oracle.box_blur_u8(src, bad)
+    with pytest.raises(ValueError, match="InvalidSigmaValue"):
+        oracle.gaussian_blur_u8(src, (4, 4), (1.0, 1.0))
