@@ -318,6 +318,49 @@ def warp_perspective_u8(src: Image, dst: Image, m: Sequence[float]) -> None:
     _warp_u8("warp_perspective_u8", "kb200_warp_perspective_u8", src, dst, m, 9)
 
 
+def _remap_prep(op: str, src: Image, dst: Image, map_x: Image, map_y: Image, interpolation: InterpolationMode):
+    if map_x.size() != map_y.size():   # interpolation/remap.rs:50-57
+        raise ImageError.InvalidImageSize(map_x.rows(), map_x.cols(), map_y.rows(), map_y.cols())
+    if dst.size() != map_x.size():
+        raise ImageError.InvalidImageSize(dst.rows(), dst.cols(), map_x.rows(), map_x.cols())
+    if interpolation not in (InterpolationMode.Bilinear, InterpolationMode.Nearest):
+        raise ImageError.UnsupportedInterpolation(interpolation)
+    dev = _prep(op, src, dst)
+    for m in (map_x, map_y):
+        if not m.is_device:
+            raise ImageError.Cuda(f"{op}: map_x and map_y must be device-resident when src/dst are on GPU")
+        if m.data.device != dev:
+            raise ImageError.DeviceMismatch()
+        _expect_dtype(m, torch.float32, "map")
+        if m.num_channels() != 1 or m.batch != 1:
+            raise ImageError.InvalidChannelShape(m.numel(), m.cols() * m.rows())
+    return dev, _same_batch(src, dst)
+
+
+def remap(src: Image, dst: Image, map_x: Image, map_y: Image, interpolation: InterpolationMode) -> None:
+    """interpolation/remap.rs:43 — dst[y,x] = sample(src, map_x[y,x], map_y[y,x]) (f32, 3 channels on the device);
+    coordinates outside the source give 0.  The maps are shared by every image of a batch."""
+    dev, n = _remap_prep("remap", src, dst, map_x, map_y, interpolation)
+    _expect_dtype(src, torch.float32, "src"); _expect_dtype(dst, torch.float32, "dst")
+    if src.num_channels() != 3 or dst.num_channels() != 3:
+        raise ImageError.Cuda("CUDA remap supports 3-channel f32 images only; move the images to the host (Image::to_host) to use the CPU path")
+    _check(_lib.lib().kb200_remap_f32_c3(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
+                                         map_x.data.data_ptr(), map_y.data.data_ptr(), map_x.numel(), src.cols(), src.rows(),
+                                         dst.cols(), dst.rows(), n, 1 if interpolation == InterpolationMode.Bilinear else 0))
+
+
+def remap_u8(src: Image, dst: Image, map_x: Image, map_y: Image, interpolation: InterpolationMode) -> None:
+    """interpolation/remap.rs:157 — u8 remap: Q10 bilinear sampler (as the u8 warps) or nearest, constant-0 border; bit-exact."""
+    dev, n = _remap_prep("remap_u8", src, dst, map_x, map_y, interpolation)
+    _expect_dtype(src, torch.uint8, "src"); _expect_dtype(dst, torch.uint8, "dst")
+    c = src.num_channels()
+    if c != dst.num_channels() or c not in (1, 3, 4):
+        raise ImageError.UnsupportedChannelCount(c)
+    _check(_lib.lib().kb200_remap_u8(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
+                                     map_x.data.data_ptr(), map_y.data.data_ptr(), map_x.numel(), src.cols(), src.rows(),
+                                     dst.cols(), dst.rows(), c, n, 1 if interpolation == InterpolationMode.Bilinear else 0))
+
+
 # ── filters ──────────────────────────────────────────────────────────────────
 def _filter_prep(op: str, src: Image, dst: Image):
     dev = _prep(op, src, dst)

@@ -792,6 +792,41 @@ KO_API int ko_warp_perspective_u8(const uint8_t* src, size_t sw, size_t sh, uint
     return 0;
 }
 
+// ─────────────────────────────────────────────────────────────────────────────
+// §8(f)#2 — remap (interpolation/remap.rs:43-128 f32, :157-296 u8).  Coordinates outside [0,w) x [0,h) (NaN included)
+// produce 0: that is what the u8 path does explicitly (:255-264, :283-285) and what the f32 device twin does
+// (cuda/remap.rs:80-85); the f32 CPU loop indexes unchecked there, so the defined behaviour is taken.
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API int ko_remap_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh, size_t C, const float* map_x,
+                        const float* map_y, int mode) {
+    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;
+    for (size_t i = 0; i < dw * dh; ++i) {
+        const float x = map_x[i], y = map_y[i];
+        const bool in = x >= 0.0f && x < (float)sw && y >= 0.0f && y < (float)sh;
+        for (size_t c = 0; c < C; ++c)
+            dst[i * C + c] = !in ? 0.0f : (mode == KO_BILINEAR ? bilinear_interpolation(src, sh, sw, C, x, y, c)
+                                                                : nearest_neighbor_interpolation(src, sh, sw, C, x, y, c));
+    }
+    return 0;
+}
+
+KO_API int ko_remap_u8(const uint8_t* src, size_t sw, size_t sh, uint8_t* dst, size_t dw, size_t dh, size_t C, const float* map_x,
+                       const float* map_y, int mode) {
+    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;   // UnsupportedInterpolation
+    for (size_t i = 0; i < dw * dh; ++i) {
+        const float xf = map_x[i], yf = map_y[i];
+        uint8_t* d = dst + i * C;
+        if (mode == KO_BILINEAR) sample_u8_checked(src, (int)sw, (int)sh, C, xf, yf, d);   // :249-268
+        else if (!(xf >= 0.0f && xf < (float)sw && yf >= 0.0f && yf < (float)sh)) { for (size_t c = 0; c < C; ++c) d[c] = 0; }
+        else {   // :283-291
+            const int xi = std::min(std::max(rust_f32_to_i32(roundf(xf)), 0), (int)sw - 1);
+            const int yi = std::min(std::max(rust_f32_to_i32(roundf(yf)), 0), (int)sh - 1);
+            for (size_t c = 0; c < C; ++c) d[c] = src[((size_t)yi * sw + (size_t)xi) * C + c];
+        }
+    }
+    return 0;
+}
+
 KO_API int ko_warp_perspective_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh,
                                    size_t C, const float m[9], int mode) {
     if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;

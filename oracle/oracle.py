@@ -72,6 +72,10 @@ def _declare(l: C.CDLL) -> None:
     l.ko_gaussian_blur_u8.restype = C.c_int
     l.ko_box_blur_u8.argtypes = [vp, vp, sz, sz, sz, sz, sz]
     l.ko_box_blur_u8.restype = C.c_int
+    l.ko_remap_f32.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp, vp, C.c_int]
+    l.ko_remap_f32.restype = C.c_int
+    l.ko_remap_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp, vp, C.c_int]
+    l.ko_remap_u8.restype = C.c_int
     l.ko_warp_affine_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
     l.ko_warp_affine_u8.restype = C.c_int
     l.ko_warp_perspective_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
@@ -489,4 +493,23 @@ def box_blur_u8(src: np.ndarray, ksize) -> np.ndarray:
     dst = np.zeros_like(src)
     if lib().ko_box_blur_u8(_p(src), _p(dst), rows, cols, c, ksize[0], ksize[1]) != 0:
         raise ValueError("InvalidSigmaValue")
+    return dst
+
+
+# ── remap ──────────────────────────────────────────────────
+def remap(src: np.ndarray, map_x: np.ndarray, map_y: np.ndarray, mode: int = 1) -> np.ndarray:
+    """interpolation/remap.rs:43 (f32) / :157 (u8, Q10 sampler); mode 0 = Nearest, 1 = Bilinear; 0 outside the source."""
+    mx = np.ascontiguousarray(map_x, np.float32); my = np.ascontiguousarray(map_y, np.float32)
+    dh, dw = mx.shape[:2]
+    sh, sw, c = src.shape
+    if src.dtype == np.uint8:
+        src = np.ascontiguousarray(src)
+        dst = np.full((dh, dw, c), 0xCD, np.uint8)
+        rc = lib().ko_remap_u8(_p(src), sw, sh, _p(dst), dw, dh, c, _p(mx), _p(my), mode)
+    else:
+        src = np.ascontiguousarray(src, np.float32)
+        dst = np.full((dh, dw, c), np.nan, np.float32)
+        rc = lib().ko_remap_f32(_p(src), sw, sh, _p(dst), dw, dh, c, _p(mx), _p(my), mode)
+    if rc != 0:
+        raise ValueError("UnsupportedInterpolation")
     return dst

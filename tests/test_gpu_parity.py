@@ -361,6 +361,66 @@ def test_blur_u8_errors_and_4k(kb, oracle, dev):
     np.testing.assert_array_equal(d.numpy(), oracle.gaussian_blur_u8(src, (5, 5), (1.5, 1.5)))
 
 
+def _remap_maps(dw, dh, sw, sh, kind, rng):
+    y, x = np.meshgrid(np.arange(dh, dtype=np.float32), np.arange(dw, dtype=np.float32), indexing="ij")
+    if kind == "identity":
+        return x * np.float32(sw / dw), y * np.float32(sh / dh)
+    if kind == "swirl":   # smooth distortion that leaves the image on all sides, with NaN / inf holes
+        cx, cy = np.float32(sw / 2), np.float32(sh / 2)
+        r2 = ((x - dw / 2) ** 2 + (y - dh / 2) ** 2).astype(np.float32) / np.float32(dw * dw)
+        mx = (cx + (x - dw / 2) * (1 + 1.5 * r2) * np.float32(sw / dw)).astype(np.float32)
+        my = (cy + (y - dh / 2) * (1 + 1.5 * r2) * np.float32(sh / dh)).astype(np.float32)
+        mx[0, 0] = np.nan; my[1, 1] = np.inf; mx[2, 2] = -np.inf; mx[3, 3] = sw - 0.25; my[3, 3] = sh - 0.25; mx[4, 4] = sw; my[5, 5] = -0.0
+        return mx, my
+    mx = rng.uniform(-3, sw + 3, (dh, dw)).astype(np.float32); my = rng.uniform(-3, sh + 3, (dh, dw)).astype(np.float32)
+    return mx, my
+
+
+@pytest.mark.parametrize("kind", ["identity", "swirl", "random"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_remap_f32(kb, oracle, dev, kind, mode):
+    n, sw, sh, dw, dh = 2, 64, 48, 57, 39
+    rng = np.random.default_rng(11)
+    src = np.stack([oracle.pattern_f32(sw * sh * 3, 0x91 + i).reshape(sh, sw, 3) for i in range(n)])
+    mx, my = _remap_maps(dw, dh, sw, sh, kind, rng)
+    want = np.stack([oracle.remap(src[i], mx, my, mode) for i in range(n)])
+    d = kb.Image(torch.full((n, dh, dw, 3), float("nan"), dtype=torch.float32, device=dev))
+    kb.imgproc.remap(kb.Image(cu(src, dev)), d, kb.Image(cu(mx[..., None], dev)), kb.Image(cu(my[..., None], dev)),
+                     kb.InterpolationMode.Bilinear if mode else kb.InterpolationMode.Nearest)
+    assert_f32_equal(d.numpy(), want, f"remap f32 {kind} mode={mode}")
+
+
+@pytest.mark.parametrize("kind", ["identity", "swirl", "random"])
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_remap_u8(kb, oracle, dev, kind, mode, c):
+    n, sw, sh, dw, dh = 2, 64, 48, 57, 39
+    rng = np.random.default_rng(12)
+    src = np.stack([oracle.pattern_u8(sw * sh * c, 0xA1 + i).reshape(sh, sw, c) for i in range(n)])
+    mx, my = _remap_maps(dw, dh, sw, sh, kind, rng)
+    want = np.stack([oracle.remap(src[i], mx, my, mode) for i in range(n)])
+    d = kb.Image(torch.full((n, dh, dw, c), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.remap_u8(kb.Image(cu(src, dev)), d, kb.Image(cu(mx[..., None], dev)), kb.Image(cu(my[..., None], dev)),
+                        kb.InterpolationMode.Bilinear if mode else kb.InterpolationMode.Nearest)
+    np.testing.assert_array_equal(d.numpy(), want)
+
+
+def test_remap_errors(kb, dev):
+    s = kb.Image.zeros_cuda(kb.ImageSize(8, 8), 3, torch.float32, dev)
+    d = kb.Image.zeros_cuda(kb.ImageSize(6, 5), 3, torch.float32, dev)
+    m65 = kb.Image.zeros_cuda(kb.ImageSize(6, 5), 1, torch.float32, dev)
+    m66 = kb.Image.zeros_cuda(kb.ImageSize(6, 6), 1, torch.float32, dev)
+    with pytest.raises(kb.ImageError, match="Invalid image size"):
+        kb.imgproc.remap(s, d, m65, m66, kb.InterpolationMode.Bilinear)
+    with pytest.raises(kb.ImageError, match="Invalid image size"):
+        kb.imgproc.remap(s, d, m66, m66, kb.InterpolationMode.Bilinear)
+    with pytest.raises(kb.ImageError, match="Unsupported interpolation"):
+        kb.imgproc.remap(s, d, m65, m65, kb.InterpolationMode.Bicubic)
+    host_map = kb.Image(torch.zeros((5, 6, 1), dtype=torch.float32))
+    with pytest.raises(kb.ImageError, match="device-resident"):
+        kb.imgproc.remap(s, d, host_map, m65, kb.InterpolationMode.Bilinear)
+
+
 # ── warps ────────────────────────────────────────────────────────────────────
 AFFINES = [
     ("identity", [1, 0, 0, 0, 1, 0]),

@@ -725,3 +725,40 @@ def test_box_blur_u8(oracle):
             oracle.box_blur_u8(src, bad)
     with pytest.raises(ValueError, match="InvalidSigmaValue"):
         oracle.gaussian_blur_u8(src, (4, 4), (1.0, 1.0))
+
+
+# ── §8(f)#2: remap ────────────────────────────────────────────────────────────
+def test_remap_reference_known_answers(oracle):
+    """interpolation/remap.rs:499-549 (f32 smoke), :551-612 (u8 identity, 1 and 3 channels), :613-643 (Q10 weight
+    quantisation: 0.1 -> 102/1024 -> 25), :644-672 (nearest zeroes out-of-range maps)."""
+    img = np.arange(9, dtype=np.float32).reshape(3, 3, 1)
+    out = oracle.remap(img, np.array([[0, 2], [0, 2]], np.float32), np.array([[0, 0], [2, 2]], np.float32), 1)
+    np.testing.assert_allclose(out[..., 0], [[0, 2], [6, 8]], atol=1e-6)
+    ident_x = np.array([[0, 1], [0, 1]], np.float32); ident_y = np.array([[0, 0], [1, 1]], np.float32)
+    g = np.array([1, 2, 3, 4], np.uint8).reshape(2, 2, 1)
+    np.testing.assert_array_equal(oracle.remap(g, ident_x, ident_y, 1), g)
+    rgb = np.arange(1, 13, dtype=np.uint8).reshape(2, 2, 3)
+    np.testing.assert_array_equal(oracle.remap(rgb, ident_x, ident_y, 1), rgb)
+    two = np.array([0, 255], np.uint8).reshape(1, 2, 1)
+    assert oracle.remap(two, np.array([[0.1]], np.float32), np.array([[0.0]], np.float32), 1)[0, 0, 0] == 25
+    q = np.array([10, 20, 30, 40], np.uint8).reshape(2, 2, 1)
+    out = oracle.remap(q, np.array([[0.49, 1.49], [-1.0, 0.5]], np.float32), np.array([[0.49, 0.49], [0.5, 2.0]], np.float32), 0)
+    np.testing.assert_array_equal(out[..., 0], [[10, 20], [0, 0]])
+    # NaN / inf coordinates are outside
+    bad = np.array([[np.nan, np.inf], [-np.inf, 0.5]], np.float32)
+    assert (oracle.remap(q, bad, np.zeros((2, 2), np.float32), 1)[..., 0] == [[0, 0], [0, 15]]).all()
+    assert (oracle.remap(q.astype(np.float32), bad, np.zeros((2, 2), np.float32), 1)[..., 0] == [[0, 0], [0, 15.0]]).all()
+
+
+def test_remap_equals_warp_for_an_affine_map(oracle):
+    """A map generated from an affine transform must reproduce the u8 perspective warp's sampler output wherever both
+    evaluate the same coordinate (identity homography bottom row => xf = nx * (1/1))."""
+    src = oracle.pattern_u8(40 * 30 * 3, 5).reshape(30, 40, 3)
+    H = [0.9, 0.15, 3.0, -0.1, 1.1, -2.0, 0.0, 0.0, 1.0]
+    inv = oracle.invert_homography(H).astype(np.float32)
+    y = np.arange(30, dtype=np.float32)[:, None]; x = np.arange(40, dtype=np.float32)[None, :]
+    nd = (inv[7] * y + inv[8]) + inv[6] * x
+    inv_nd = np.float32(1.0) / nd
+    mx = ((inv[1] * y + inv[2]) + inv[0] * x) * inv_nd
+    my = ((inv[4] * y + inv[5]) + inv[3] * x) * inv_nd
+    np.testing.assert_array_equal(oracle.remap(src, mx, my, 1), oracle.warp_perspective_u8(src, 40, 30, H))
