@@ -80,6 +80,22 @@ pub mod ffi {
                                                       leaf: c_int) -> c_int;
         pub fn kb200_resize_bilinear_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32,
                                         src_h: u32, dst_w: u32, dst_h: u32, channels: u32, batch: u32) -> c_int;
+        pub fn kb200_resize_fast_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32, src_h: u32,
+                                    dst_w: u32, dst_h: u32, channels: u32, batch: u32, interp: c_int) -> c_int;
+        pub fn kb200_warp_affine_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32, src_h: u32,
+                                    dst_w: u32, dst_h: u32, channels: u32, batch: u32, m: *const f32) -> c_int;
+        pub fn kb200_warp_perspective_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32,
+                                         src_h: u32, dst_w: u32, dst_h: u32, channels: u32, batch: u32, h: *const f32) -> c_int;
+        pub fn kb200_quantize_kernel_256(kernel: *const f32, n: u32, out: *mut u8);
+        pub fn kb200_gaussian_blur_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, cols: u32, rows: u32,
+                                      channels: u32, batch: u32, ksize_x: u32, ksize_y: u32, sigma_x: f32, sigma_y: f32) -> c_int;
+        pub fn kb200_box_blur_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, cols: u32, rows: u32,
+                                 channels: u32, batch: u32, ksize_x: u32, ksize_y: u32) -> c_int;
+        pub fn kb200_remap_f32_c3(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize, map_x: *const f32,
+                                  map_y: *const f32, map_len: usize, src_w: u32, src_h: u32, dst_w: u32, dst_h: u32, batch: u32, interp: c_int) -> c_int;
+        pub fn kb200_remap_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, map_x: *const f32,
+                              map_y: *const f32, map_len: usize, src_w: u32, src_h: u32, dst_w: u32, dst_h: u32, channels: u32, batch: u32,
+                              interp: c_int) -> c_int;
         pub fn kb200_warp_affine_f32_c3(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize, src_w: u32,
                                         src_h: u32, dst_w: u32, dst_h: u32, batch: u32, m: *const f32, interp: c_int) -> c_int;
         pub fn kb200_warp_perspective_f32_c3(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize,
@@ -294,4 +310,41 @@ impl Drop for HostPipeline {
     fn drop(&mut self) {
         unsafe { ffi::kb200_host_pipeline_destroy(self.raw) }
     }
+}
+
+
+/// Replaces `launch_warp_perspective_u8_bilinear_cuda` (cuda/warp_perspective_u8.rs:181).  NOTE: takes the FORWARD
+/// homography like the public operator (the reference launcher takes the inverse; the adapter inverts) — call it from
+/// `warp_perspective_u8_cuda` with `m`, not `m_inv`.
+#[allow(clippy::too_many_arguments)]
+pub fn launch_warp_perspective_u8_bilinear_cuda(
+    ctx: &Arc<CudaContext>, stream: &Arc<CudaStream>, src: &CudaSlice<u8>, dst: &mut CudaSlice<u8>, m: &[f32; 9],
+    src_width: u32, src_height: u32, dst_width: u32, dst_height: u32, channels: u32, _block_dim: Option<(u32, u32)>,
+) -> Result<(), Kb200Error> {
+    bind(ctx)?;
+    let (sp, _g0) = src.device_ptr(stream);
+    let (src_len, dst_len) = (src.len(), dst.len());
+    let (dp, _g1) = dst.device_ptr_mut(stream);
+    check(unsafe {
+        ffi::kb200_warp_perspective_u8(stream.cu_stream() as *mut c_void, sp as *const u8, src_len, dp as *mut u8, dst_len,
+                                       src_width, src_height, dst_width, dst_height, channels, 1, m.as_ptr())
+    })
+}
+
+/// Replaces `launch_remap_bilinear_cuda` (cuda/remap.rs): f32, 3 channels, maps of dst_w*dst_h f32 each.
+#[allow(clippy::too_many_arguments)]
+pub fn launch_remap_bilinear_cuda(
+    ctx: &Arc<CudaContext>, stream: &Arc<CudaStream>, src: &CudaSlice<f32>, dst: &mut CudaSlice<f32>, map_x: &CudaSlice<f32>,
+    map_y: &CudaSlice<f32>, src_width: u32, src_height: u32, dst_width: u32, dst_height: u32, _block_dim: Option<(u32, u32)>,
+) -> Result<(), Kb200Error> {
+    bind(ctx)?;
+    let (sp, _g0) = src.device_ptr(stream);
+    let (mx, _g2) = map_x.device_ptr(stream);
+    let (my, _g3) = map_y.device_ptr(stream);
+    let (src_len, dst_len, map_len) = (src.len(), dst.len(), map_x.len().min(map_y.len()));
+    let (dp, _g1) = dst.device_ptr_mut(stream);
+    check(unsafe {
+        ffi::kb200_remap_f32_c3(stream.cu_stream() as *mut c_void, sp as *const f32, src_len, dp as *mut f32, dst_len, mx as *const f32,
+                                my as *const f32, map_len, src_width, src_height, dst_width, dst_height, 1, 1)
+    })
 }
