@@ -308,6 +308,33 @@ def op_table(kb, dev, peak_gbs: float, quick: bool) -> dict:
     u8 = kb.Image(torch.randint(0, 256, (n * 4, h, w, 3), dtype=torch.uint8, device=dev, generator=g))
     ms = time_launches(lambda: kb.imgproc.std_mean_sums(u8), it, wu, st)
     rec("std_mean_4k_u8", ms, n * 4 * w * h / 1e6, n * 4 * w * h * 3, f"batch {4 * n}")
+    # SURVEY §8(f) "next" rows (u8 twins, remap): functional + bit-exact this round, not yet tuned
+    nb = n                                   # reuse the first `n` u8 frames
+    s8 = kb.Image(u8.data[:nb])
+    d8 = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.uint8, dev, batch=nb)
+    half = kb.Image.zeros_cuda(kb.ImageSize(w // 2, h // 2), 3, torch.uint8, dev, batch=nb)
+    px = nb * w * h
+    ms = time_launches(lambda: kb.imgproc.resize_fast_u8(s8, half, kb.InterpolationMode.Bilinear), it, wu, st)
+    rec("next_resize_fast_u8_pyrdown_4k_to_1080p", ms, px / 4 / 1e6, px * 3 + px * 3 // 4, f"batch {nb}")
+    ms = time_launches(lambda: kb.imgproc.warp_perspective_u8(s8, d8, H), it, wu, st)
+    rec("next_warp_perspective_u8_4k", ms, px / 1e6, px * 3 * 2, f"batch {nb}")
+    ms = time_launches(lambda: kb.imgproc.warp_affine_u8(s8, d8, M), it, wu, st)
+    rec("next_warp_affine_u8_rot30_4k", ms, px / 1e6, px * 3 * 2, f"batch {nb}")
+    ms = time_launches(lambda: kb.imgproc.gaussian_blur_u8(s8, d8, (5, 5), (1.5, 1.5)), it, wu, st)
+    rec("next_gaussian_blur_u8_5x5_4k", ms, px / 1e6, px * 3 * 2, f"batch {nb}")
+    yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+    r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / float(w * w)
+    mx = kb.Image((w / 2 + (xx - w / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())
+    my = kb.Image((h / 2 + (yy - h / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())
+    del yy, xx, r2
+    ms = time_launches(lambda: kb.imgproc.remap_u8(s8, d8, mx, my, kb.InterpolationMode.Bilinear), it, wu, st)
+    rec("next_remap_u8_4k", ms, px / 1e6, px * 3 * 2 + w * h * 8, f"batch {nb}; radial-distortion map shared by the batch")
+    del u8, s8, d8, half
+    nf = max(2, nb // 2)
+    sf = kb.Image(torch.rand((nf, h, w, 3), dtype=torch.float32, device=dev, generator=g))
+    df = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=nf)
+    ms = time_launches(lambda: kb.imgproc.remap(sf, df, mx, my, kb.InterpolationMode.Bilinear), it, wu, st)
+    rec("next_remap_f32_4k", ms, nf * w * h / 1e6, nf * w * h * 24 + w * h * 8, f"batch {nf}")
     return out
 
 

@@ -1,26 +1,14 @@
 #!/bin/bash
 # Scratch driver for one gpurun call (edited per experiment; the durable scripts are tools/run_op.py and bench.py).
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -k "remap" 2>&1 | tail -3
-python - <<'PY'
-import torch, numpy as np, kornia_rs_b200 as kb
-dev=torch.device("cuda:0")
-n,w,h=8,3840,2160
-y,x=torch.meshgrid(torch.arange(h,device=dev,dtype=torch.float32),torch.arange(w,device=dev,dtype=torch.float32),indexing="ij")
-r2=((x-w/2)**2+(y-h/2)**2)/(w*w)
-mx=kb.Image((w/2+(x-w/2)*(1+0.05*r2)).unsqueeze(-1).contiguous()); my=kb.Image((h/2+(y-h/2)*(1+0.05*r2)).unsqueeze(-1).contiguous())
-for name,dt,c in [("remap f32",torch.float32,3),("remap_u8",torch.uint8,3)]:
-    src=kb.Image(torch.rand((n,h,w,c),device=dev) if dt==torch.float32 else torch.randint(0,256,(n,h,w,c),dtype=torch.uint8,device=dev))
-    dst=kb.Image.zeros_cuda(kb.ImageSize(w,h),c,dt,dev,batch=n)
-    fn=(lambda: kb.imgproc.remap(src,dst,mx,my,kb.InterpolationMode.Bilinear)) if dt==torch.float32 else (lambda: kb.imgproc.remap_u8(src,dst,mx,my,kb.InterpolationMode.Bilinear))
-    for _ in range(3): fn()
-    torch.cuda.synchronize()
-    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): fn()
-    e1.record(); torch.cuda.synchronize()
-    ms=e0.elapsed_time(e1)/10
-    es=4 if dt==torch.float32 else 1
-    print(f"{name} 4K x{n}: {ms:.4f} ms  {n*w*h/1e6/ms*1e3:.0f} Mpix/s  src+dst+maps {(2*n*w*h*c*es+n*w*h*8)/ms/1e6:.0f} GB/s")
-    del src,dst
-PY
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref_r1.json 2>gpurun_out/bench_ref.err; cat gpurun_out/bench_ref_r1.json | cut -c1-300
+python bench.py --steps 100 --warmup 10 2>gpurun_out/b.err > gpurun_out/bench_r1.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1.json'))
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e']['ms_per_step'], d['clocks'])
+for k,v in d.get('ops',{}).items(): print(k, v if not isinstance(v,dict) else {a:b for a,b in v.items() if a in ('ms','frac','mpix_s')})
+print(d.get('cpu_baseline'))"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kb200 --kernel-name-base demangled -c 600 --csv \
+  --log-file gpurun_out/launches_r1.csv python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+wc -l gpurun_out/launches_r1.csv
