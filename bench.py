@@ -44,6 +44,25 @@ METRIC, UNIT = "Mpix/s (dst pixels) fused bilinear resize 4K->720p RGB u8->f32 C
 WORKLOAD = "configs[1]: fused bilinear resize+normalize 3840x2160->1280x720 RGB u8 HWC -> f32 CHW, batch=64 per GPU"
 
 
+# stdout carries exactly ONE JSON line.  Native libraries write banners to fd 1 (NCCL prints its version there when
+# NCCL_DEBUG is set in the environment), so fd 1 is pointed at stderr for the whole run and the line goes out through
+# a saved duplicate of the original stdout.
+_JSON_FD = None
+
+
+def claim_stdout() -> None:
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -204,7 +223,7 @@ def run_reference_arm(args) -> None:
                                    "resize_normalize_to_tensor_u8_to_f32_bilinear (AVX2+FMA leaf), OpenMP 8-row tasks"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_sample(budget_s: float = 12.0) -> dict:
@@ -349,6 +368,7 @@ def main() -> None:
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer (e2e) leg; the line then has e2e = null")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference_arm(args)
@@ -487,7 +507,7 @@ def main() -> None:
             line["cpu_baseline"] = cpu
         if ops is not None:
             line["ops"] = ops
-        print(json.dumps(line), flush=True)
+        emit(line)
     if kb.dist.is_initialized():
         import torch.distributed as td
 
