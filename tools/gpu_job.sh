@@ -1,14 +1,9 @@
 #!/bin/bash
 # Scratch driver for one gpurun call (edited per experiment; the durable scripts are tools/run_op.py and bench.py).
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref_r1.json 2>gpurun_out/bench_ref.err; cat gpurun_out/bench_ref_r1.json | cut -c1-300
-python bench.py --steps 100 --warmup 10 2>gpurun_out/b.err > gpurun_out/bench_r1.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1.json'))
-print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e']['ms_per_step'], d['clocks'])
-for k,v in d.get('ops',{}).items(): print(k, v if not isinstance(v,dict) else {a:b for a,b in v.items() if a in ('ms','frac','mpix_s')})
-print(d.get('cpu_baseline'))"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kb200 --kernel-name-base demangled -c 600 --csv \
-  --log-file gpurun_out/launches_r1.csv python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-wc -l gpurun_out/launches_r1.csv
+python -m pytest tests -m gpu -x -q -k "warp and not u8" 2>&1 | tail -2
+for op in warp affine; do
+  echo -n "gather-x4 "; KB200_WARP_IMPL=1 python tools/run_op.py $op 30
+  echo -n "old-tiled "; KB200_WARP_IMPL=2 python tools/run_op.py $op 30
+  echo -n "tiled-x4  "; python tools/run_op.py $op 30
+done
