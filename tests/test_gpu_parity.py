@@ -848,3 +848,43 @@ def test_div255_identity_exhaustive(kb, dev):
     torch.cuda.synchronize()
     print("div255 mismatches:", int(out.item()))
     assert int(out.item()) == 0
+
+
+def test_entry_points_are_cuda_graph_capturable(kb, oracle, dev):
+    """The launchers only enqueue on the caller's stream and never allocate or synchronise, so — once warm — a sequence of
+    them can be captured into a CUDA graph and replayed (the convention of the reference launchers, resize/cuda.rs:103-109;
+    kornia-py captures its preprocess pipeline this way, cuda_ext/mod.rs:1726-1790)."""
+    sw, sh, dw, dh = 384, 216, 128, 72
+    src8 = np.stack([oracle.pattern_u8(sw * sh * 3, 0x3000 + i).reshape(sh, sw, 3) for i in range(2)])
+    scale, bias = oracle.normalize_params_from_mean_std([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    t8 = cu(src8, dev)
+    fused = torch.empty((2, 3, dh, dw), dtype=torch.float32, device=dev)
+    f32 = kb.Image(cu(oracle.pattern_f32(256 * 96 * 3).reshape(96, 256, 3), dev))
+    blur = kb.Image.zeros_cuda(kb.ImageSize(256, 96), 3, torch.float32, dev)
+    edge = kb.Image.zeros_cuda(kb.ImageSize(256, 96), 3, torch.float32, dev)
+    warped = kb.Image.zeros_cuda(kb.ImageSize(256, 96), 3, torch.float32, dev)
+    H = [1.02, 0.03, -4.0, -0.03, 1.01, 2.5, 2.0e-5, 1.2e-5, 1.0]
+    u8w = kb.Image.zeros_cuda(kb.ImageSize(sw, sh), 3, torch.uint8, dev, batch=2)
+
+    def pipeline():
+        kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(t8, dw, dh, scale, bias, out=fused)
+        kb.imgproc.gaussian_blur(f32, blur, (5, 5), (1.5, 1.5))
+        kb.imgproc.sobel(blur, edge, 3)
+        kb.imgproc.warp_perspective(f32, warped, H, kb.InterpolationMode.Bilinear)
+        kb.imgproc.warp_perspective_u8(kb.Image(t8), u8w, [1.0, 0.02, -3.0, -0.01, 1.0, 2.0, 1e-5, 0.0, 1.0])
+
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        pipeline()                       # warm: function attributes, occupancy queries, tensor-map encoder lookup
+        side.synchronize()
+        want = [t.clone() for t in (fused, blur.data, edge.data, warped.data, u8w.data)]
+        for t in (fused, blur.data, edge.data, warped.data, u8w.data):
+            t.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            pipeline()
+        for _ in range(2):
+            g.replay()
+        side.synchronize()
+    for got, ref in zip((fused, blur.data, edge.data, warped.data, u8w.data), want):
+        assert torch.equal(got, ref)
