@@ -499,7 +499,11 @@ def main() -> None:
             "e2e": e2e,
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "fused_resize (resize_fused.cu)",
+                         "traffic": traffic, "frac_of_traffic": (traffic / (ms_launch * 1e-3) / 1e9 / peak_gbs) if traffic else None,
+                         "note": "algorithmic bytes count all four taps per pixel (SURVEY 8(d)); at 3:1 three have weight exactly 0 and are "
+                                 "not fetched, so the bytes moved (traffic) are below the algorithmic bytes and frac can exceed 1; "
+                                 "frac_of_traffic = bytes actually moved / time / peak",
+                         "peak_source": peak_src, "kernel": "fused_rows_kernel (resize_fused.cu)",
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch},
             "clocks": clocks,
         }

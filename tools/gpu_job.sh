@@ -1,3 +1,3 @@
 #!/bin/bash
 # Scratch driver for one gpurun call (edited per experiment; the durable scripts are tools/run_op.py and bench.py).
-python -m pytest tests -m gpu -x -q -k "graph_capturable" 2>&1 | tail -15
+python tools/e2e_sweep.py 2>&1 | tail -14
