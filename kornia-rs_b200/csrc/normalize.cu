@@ -162,11 +162,10 @@ __global__ void __launch_bounds__(256) std_mean_kernel(const uint8_t* __restrict
     const uint32_t ph = (uint32_t)(q % 3);
     uint32_t pending = 0;
     const uint4* v4 = reinterpret_cast<const uint4*>(src);
-    for (; q < nvec; q += stride) {
-        const uint4 v = ldg_stream_u4(v4 + q);
+    // byte j of word kk is relative channel (kk + j) % 3.  DP4A does the byte sums: Σ b·sel for the plain sums,
+    // Σ b·(b & mask) for the squares — 3 LOP + 6 IDP4A per word instead of ~20 scalar ops.
+    auto accumulate = [&](const uint4& v) {
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        // byte j of word kk is relative channel (kk + j) % 3.  DP4A does the byte sums: Σ b·sel for the plain sums,
-        // Σ b·(b & mask) for the squares — 3 LOP + 6 IDP4A per word instead of ~20 scalar ops.
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
@@ -179,11 +178,24 @@ __global__ void __launch_bounds__(256) std_mean_kernel(const uint8_t* __restrict
                 q32[r] = __dp4a(w[kk], w[kk] & mask, q32[r]);
             }
         }
-        if (++pending == 8192u) {
+    };
+    auto flush = [&]() {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) { s64[c] += s32[c]; q64[c] += q32[c]; s32[c] = 0; q32[c] = 0; }
-            pending = 0;
-        }
+        for (int c = 0; c < 3; ++c) { s64[c] += s32[c]; q64[c] += q32[c]; s32[c] = 0; q32[c] = 0; }
+        pending = 0;
+    };
+    // four independent 16-B loads in flight per thread (the one-load loop is latency-bound, see normalize_mean_std_c3_vec);
+    // the stride is a multiple of 3, so all four vectors share the thread's channel phase
+    for (; q + 3 * stride < nvec; q += 4 * stride) {
+        const uint4 a = ldg_stream_u4(v4 + q), b = ldg_stream_u4(v4 + q + stride), c = ldg_stream_u4(v4 + q + 2 * stride),
+                    d = ldg_stream_u4(v4 + q + 3 * stride);
+        accumulate(a); accumulate(b); accumulate(c); accumulate(d);
+        pending += 4;
+        if (pending >= 8192u) flush();   // 255^2 * 6 bytes * 8192 vectors < 2^32
+    }
+    for (; q < nvec; q += stride) {
+        accumulate(ldg_stream_u4(v4 + q));
+        if (++pending >= 8192u) flush();
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) { s64[c] += s32[c]; q64[c] += q32[c]; }

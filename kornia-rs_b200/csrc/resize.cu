@@ -136,6 +136,33 @@ __global__ void __launch_bounds__(256) pyrdown_2x_rgb_u8_kernel(const uint8_t* _
     for (int ch = 0; ch < 3; ++ch) d[ch] = (uint8_t)(((uint32_t)r0[ch] + r0[3 + ch] + r1[ch] + r1[3 + ch] + 2u) >> 2);
 }
 
+// Word-granular pyrdown: a thread produces 4 destination pixels (12 bytes = 3 words) from 2 x 24 source bytes read as
+// 6 + 6 aligned words — 15 memory instructions per 4 pixels instead of 60 (the byte version is LSU-bound at 0.48 of the
+// roofline).  Needs sw % 8 == 0 (row = whole 24-byte groups, 4-byte aligned) and 4-byte aligned bases.
+__global__ void __launch_bounds__(256) pyrdown_2x_rgb_u8_w4_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t sw,
+                                                                   uint32_t sh, uint32_t dw, uint32_t dh) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 destination pixels
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    const uint32_t groups = dw >> 2;
+    if (g >= groups || y >= dh) return;
+    const uint32_t srow_w = sw * 3u / 4u, drow_w = dw * 3u / 4u;   // words per row
+    const uint32_t* r0 = src + ((size_t)blockIdx.z * sh + 2u * y) * srow_w + 6u * g;
+    const uint32_t* r1 = r0 + srow_w;
+    uint32_t a[6], b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { a[k] = __ldg(r0 + k); b[k] = __ldg(r1 + k); }
+    auto byte_of_row = [](const uint32_t (&w)[6], int k) -> uint32_t { return (w[k >> 2] >> (8 * (k & 3))) & 0xFFu; };
+    uint32_t out[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int o = 0; o < 12; ++o) {                 // destination byte o: pixel o / 3, channel o % 3
+        const int k = 6 * (o / 3) + (o % 3);       // first source byte; its horizontal neighbour is k + 3
+        const uint32_t v = (byte_of_row(a, k) + byte_of_row(a, k + 3) + byte_of_row(b, k) + byte_of_row(b, k + 3) + 2u) >> 2;
+        out[o >> 2] |= v << (8 * (o & 3));
+    }
+    uint32_t* d = dst + ((size_t)blockIdx.z * dh + y) * drow_w + 3u * g;
+    d[0] = out[0]; d[1] = out[1]; d[2] = out[2];
+}
+
 // resize/kernels.rs:168-181 + :274-281 + resize/pyramid.rs:50-120.
 // Horizontal stage H(row)[X]: X = 2j+1 -> (a + avg + 1) >> 1, X = 2j+2 -> (b + avg + 1) >> 1 with a = row[j], b = row[j+1],
 // avg = (a + b + 1) >> 1; X = 0 and X = 2sw-1 copy the edge pixel.  Vertical stage: row 2I+1 -> blend(H(I), H(I+1)),
@@ -340,6 +367,11 @@ KB200_API int kb200_resize_fast_u8(kb200_stream_t stream, const uint8_t* src, si
     cudaStream_t s = as_stream(stream);
     dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
     if (interp == KB200_INTERP_BILINEAR && C == 3 && sw == 2 * dw && sh == 2 * dh && sw >= 2 && sh >= 2) {
+        if ((sw & 7u) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0) {
+            dim3 wgrid(div_up(dw / 4, 32), div_up(dh, 8), batch);
+            pyrdown_2x_rgb_u8_w4_kernel<<<wgrid, block, 0, s>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), sw, sh, dw, dh);
+            return check_launch("pyrdown_2x_rgb_u8_w4_kernel");
+        }
         pyrdown_2x_rgb_u8_kernel<<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh);
         return check_launch("pyrdown_2x_rgb_u8_kernel");
     }
