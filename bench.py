@@ -335,6 +335,10 @@ def op_table(kb, dev, peak_gbs: float, quick: bool) -> dict:
     px = nb * w * h
     ms = time_launches(lambda: kb.imgproc.resize_fast_u8(s8, half, kb.InterpolationMode.Bilinear), it, wu, st)
     rec("next_resize_fast_u8_pyrdown_4k_to_1080p", ms, px / 4 / 1e6, px * 3 + px * 3 // 4, f"batch {nb}")
+    third = kb.Image.zeros_cuda(kb.ImageSize(w // 3, h // 3), 3, torch.uint8, dev, batch=nb)
+    ms = time_launches(lambda: kb.imgproc.resize_fast_u8(s8, third, kb.InterpolationMode.Bilinear), it, wu, st)
+    rec("next_resize_fast_u8_4k_to_720p", ms, px / 9 / 1e6, px * 3 * 4 // 9 + px * 3 // 9, f"batch {nb}; u8 twin of config 2 (4/9 of the source + destination)")
+    del third
     ms = time_launches(lambda: kb.imgproc.warp_perspective_u8(s8, d8, H), it, wu, st)
     rec("next_warp_perspective_u8_4k", ms, px / 1e6, px * 3 * 2, f"batch {nb}")
     ms = time_launches(lambda: kb.imgproc.warp_affine_u8(s8, d8, M), it, wu, st)

@@ -231,6 +231,30 @@ __global__ void __launch_bounds__(256) resize_bilinear_u8_kernel(const uint8_t* 
     }
 }
 
+// Exact 3:1 downscale (2160p -> 720p, 1080p -> 360p): the f64 half-pixel tap is s = 3i + 1 with fraction exactly 0 on
+// both axes, so the Q28 blend returns p00 unchanged — the result is the centre pixel of every 3x3 block.  A thread
+// copies 4 destination pixels: 36 source bytes read as 9 aligned words, bytes 3..5, 12..14, 21..23, 30..32 packed into
+// 3 words (12 memory instructions per 4 pixels instead of 60; one source row in three is read).
+__global__ void __launch_bounds__(256) resize_bilinear_u8_c3_3to1_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                                         uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;   // group of 4 destination pixels
+    const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (g >= (dw >> 2) || y >= dh) return;
+    const uint32_t srow_w = sw * 3u / 4u, drow_w = dw * 3u / 4u;
+    const uint32_t* r = src + ((size_t)blockIdx.z * sh + 3u * y + 1u) * srow_w + 9u * g;
+    uint32_t w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = __ldg(r + k);
+    uint32_t out[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int o = 0; o < 12; ++o) {                  // destination byte o: pixel o / 3, channel o % 3
+        const int k = 9 * (o / 3) + 3 + (o % 3);    // source pixel 3*px + 1
+        out[o >> 2] |= ((w[k >> 2] >> (8 * (k & 3))) & 0xFFu) << (8 * (o & 3));
+    }
+    uint32_t* d = dst + ((size_t)blockIdx.z * dh + y) * drow_w + 3u * g;
+    d[0] = out[0]; d[1] = out[1]; d[2] = out[2];
+}
+
 // resize/nearest.rs:18-21: clamp(floor((i + 0.5) * scale)) in f64
 __device__ __forceinline__ uint32_t nearest_index_f64(uint32_t i, double scale, uint32_t src_len) {
     const long long v = (long long)floor(__dmul_rn((double)i + 0.5, scale));
@@ -348,6 +372,11 @@ KB200_API int kb200_resize_bilinear_u8(kb200_stream_t stream, const uint8_t* src
     const double scale_x = (double)sw / (double)dw, scale_y = (double)sh / (double)dh;
     dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
     cudaStream_t s = as_stream(stream);
+    if (C == 3 && sw == 3 * dw && sh == 3 * dh && (dw & 3u) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0) {
+        dim3 wgrid(div_up(dw / 4, 32), div_up(dh, 8), batch);
+        resize_bilinear_u8_c3_3to1_kernel<<<wgrid, block, 0, s>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), sw, sh, dw, dh);
+        return check_launch("resize_bilinear_u8_c3_3to1_kernel");
+    }
     if (C == 1) resize_bilinear_u8_kernel<1><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
     else if (C == 3) resize_bilinear_u8_kernel<3><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
     else resize_bilinear_u8_kernel<4><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, scale_x, scale_y);
