@@ -109,6 +109,124 @@ __global__ void __launch_bounds__(256) blur_u8_tile_kernel(const uint8_t* __rest
     }
 }
 
+// ── word-granular variant ────────────────────────────────────────────────────────────────────
+// ncu-free arithmetic on the kernel above: ~15 LSU operations per output byte (byte gathers, one LDS.U8 per tap per
+// byte, byte stores) against 1.5 B of DRAM traffic per byte — LSU-bound at 0.12 of the roofline.  Here every access is
+// a 32-bit word and four bytes are filtered at once in two 16-bit lanes per register:
+//   e = w & 0x00FF00FF, o = (w >> 8) & 0x00FF00FF;  acc_e += e * k, acc_o += o * k
+// A lane never overflows: Σ byte·k <= 255 · Σk = 255 · 256 < 2^16 (the host checks Σk <= 256), and the Q8 rounding
+// (+128, >> 8) is applied per lane, so each byte gets exactly the reference's u32 arithmetic.  The binomial path is
+// the per-byte rounded average (a | b) - (((a ^ b) >> 1) & 0x7F7F7F7F) == (a + b + 1) >> 1.
+// The staged tile keeps the global word alignment of its first byte: tile byte j lives at shared byte j + SH0 with
+// SH0 = (-(K/2)*C) mod 4 (a tile starts at a multiple of 32 pixels), so interior tiles are gathered with aligned
+// LDG.32 / STS.32 and a tap's four bytes are one funnel shift of two neighbouring words at a compile-time offset.
+// Needs cols*C % 4 == 0 and 4-byte aligned images; anything else uses the byte kernel.
+__device__ __forceinline__ uint32_t avg4_round_up(uint32_t a, uint32_t b) { return (a | b) - (((a ^ b) >> 1) & 0x7F7F7F7Fu); }
+
+static constexpr int U8W_TW = 64, U8W_TH = 64;   // word kernel: larger tiles amortise the two block-wide phase changes and the halo rows
+
+template <int C, int K>
+__global__ void __launch_bounds__(256) blur_u8_tile_w_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t cols,
+                                                             uint32_t rows, uint32_t tiles_x, uint32_t tiles_y,
+                                                             const __grid_constant__ U8Taps T) {
+    constexpr int HX = K / 2, HY = K / 2;
+    constexpr int SH0 = ((-(HX * C)) % 4 + 4) % 4;
+    constexpr int IN_WPX = U8W_TW + 2 * HX, IN_H = U8W_TH + 2 * HY;
+    constexpr int IN_WW = (IN_WPX * C + SH0 + 3) / 4 + 1;        // words per staged row (+1: the last funnel shift reads one word further)
+    constexpr int MID_WW = U8W_TW * C / 4;                       // words per intermediate row
+    constexpr int NW = (SH0 + (K - 1) * C + 4 + 3) / 4 + 1;      // words covering all taps of one 4-byte output
+    extern __shared__ uint32_t u8w_smem[];
+    uint32_t* in = u8w_smem;                                     // [IN_H][IN_WW]
+    uint32_t* mid = u8w_smem + IN_H * IN_WW;                     // [IN_H][MID_WW]
+    uint32_t kx[K], ky[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { kx[k] = T.kx[k]; ky[k] = T.ky[k]; }
+    const bool binomial = T.binomial != 0;
+    const uint32_t t = blockIdx.x;
+    const uint32_t img = t / (tiles_x * tiles_y), tt = t - img * tiles_x * tiles_y;
+    const int x0 = (int)(tt % tiles_x) * U8W_TW, y0 = (int)(tt / tiles_x) * U8W_TH;
+    const uint32_t rowb = cols * C;                              // bytes per image row, multiple of 4
+    const uint8_t* s = src + (size_t)img * rowb * rows;
+    uint8_t* d = dst + (size_t)img * rowb * rows;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    const bool interior_x = x0 - HX >= 0 && x0 + U8W_TW + HX <= (int)cols;
+    // ── gather (rows clamped; columns clamped only on edge tiles) ──
+    if (interior_x) {
+        const int abase = (x0 - HX) * C - SH0;                   // global byte of shared word 0: multiple of 4, >= -3
+        for (int r = ty; r < IN_H; r += 8) {
+            const int sy = min(max(y0 - HY + r, 0), (int)rows - 1);
+            const uint32_t* srow = reinterpret_cast<const uint32_t*>(s + (size_t)sy * rowb);
+            for (int w = tx; w < IN_WW; w += 32) {
+                const int gb = abase + 4 * w;                    // first global byte of this word
+                // the first word may start before the row (SH0 bytes of slack) and the last may end after it: those
+                // bytes are never used by a tap, so any in-bounds word will do
+                const int gw = min(max(gb, 0), (int)rowb - 4) >> 2;
+                in[r * IN_WW + w] = __ldg(srow + gw);
+            }
+        }
+    } else {
+        uint8_t* inb = reinterpret_cast<uint8_t*>(in);
+        for (int r = ty; r < IN_H; r += 8) {
+            const int sy = min(max(y0 - HY + r, 0), (int)rows - 1);
+            const uint8_t* srow = s + (size_t)sy * rowb;
+            for (int p = tx; p < IN_WPX; p += 32) {
+                const int sx = min(max(x0 - HX + p, 0), (int)cols - 1);
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) inb[r * IN_WW * 4 + SH0 + p * C + ch] = srow[sx * C + ch];
+            }
+        }
+    }
+    __syncthreads();
+    // ── H pass: 4 output bytes per item ──
+    for (int i = tid; i < IN_H * MID_WW; i += 256) {
+        const int r = i / MID_WW, q = i - r * MID_WW;
+        const uint32_t* ip = in + r * IN_WW + q;
+        uint32_t W[NW];
+#pragma unroll
+        for (int n = 0; n < NW; ++n) W[n] = ip[n];
+        uint32_t v;
+        if (binomial) {
+            uint32_t x[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { constexpr int dummy = 0; (void)dummy; const int off = SH0 + k * C; x[k] = __funnelshift_r(W[off >> 2], W[(off >> 2) + 1], 8 * (off & 3)); }
+            v = avg4_round_up(avg4_round_up(x[0], x[1]), avg4_round_up(x[1], x[2]));
+        } else {
+            uint32_t ae = 0x00800080u, ao = 0x00800080u;         // + 128 per lane
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int off = SH0 + k * C;
+                const uint32_t x = __funnelshift_r(W[off >> 2], W[(off >> 2) + 1], 8 * (off & 3));
+                ae += (x & 0x00FF00FFu) * kx[k];
+                ao += ((x >> 8) & 0x00FF00FFu) * kx[k];
+            }
+            v = ((ae >> 8) & 0x00FF00FFu) | (ao & 0xFF00FF00u);
+        }
+        mid[r * MID_WW + q] = v;
+    }
+    __syncthreads();
+    // ── V pass -> global words ──
+    const int nwords = min(MID_WW, (int)((cols - (uint32_t)x0) * C / 4));   // valid words of this tile row
+    for (int i = tid; i < U8W_TH * MID_WW; i += 256) {
+        const int r = i / MID_WW, q = i - r * MID_WW;
+        const int gy = y0 + r;
+        if (gy >= (int)rows || q >= nwords) continue;
+        const uint32_t* mp = mid + r * MID_WW + q;
+        uint32_t v;
+        if (binomial) v = avg4_round_up(avg4_round_up(mp[0], mp[MID_WW]), avg4_round_up(mp[MID_WW], mp[2 * MID_WW]));
+        else {
+            uint32_t ae = 0x00800080u, ao = 0x00800080u;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint32_t x = mp[k * MID_WW];
+                ae += (x & 0x00FF00FFu) * ky[k];
+                ao += ((x >> 8) & 0x00FF00FFu) * ky[k];
+            }
+            v = ((ae >> 8) & 0x00FF00FFu) | (ao & 0xFF00FF00u);
+        }
+        reinterpret_cast<uint32_t*>(d + (size_t)gy * rowb + (size_t)x0 * C)[q] = v;
+    }
+}
+
 // filter/ops.rs:759-770
 static void quantize_kernel_256(const float* k, int n, uint8_t* out) {
     uint32_t sum = 0;
@@ -145,6 +263,33 @@ static int launch_blur_u8(cudaStream_t s, const uint8_t* src, size_t src_len, ui
         kern<<<(unsigned)ntiles, 256, smem, s>>>(src, dst, cols, rows, tiles_x, tiles_y, T);
         return check_launch("blur_u8_tile_kernel");
     };
+    // word-granular path: whole-word rows, aligned images, K in {3,5,7} on both axes, tap sums that cannot overflow a 16-bit lane
+    {
+        uint32_t sx = 0, sy = 0;
+        for (int k = 0; k < T.kxn; ++k) sx += T.kx[k];
+        for (int k = 0; k < T.kyn; ++k) sy += T.ky[k];
+        const bool word_ok = ((size_t)cols * C) % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0 &&
+                             T.kxn == T.kyn && (T.binomial || (sx <= 256 && sy <= 256)) && cols >= 4;
+        if (word_ok && (T.kxn == 3 || T.kxn == 5 || T.kxn == 7)) {
+            auto gow = [&](auto kern, int K) -> int {
+                const int hx = K / 2;
+                const int sh0 = ((-(hx * (int)C)) % 4 + 4) % 4;
+                const size_t in_ww = ((U8W_TW + 2 * hx) * C + sh0 + 3) / 4 + 1, mid_ww = U8W_TW * C / 4;
+                const size_t smem_w = (size_t)(U8W_TH + 2 * hx) * (in_ww + mid_ww) * 4;
+                const uint32_t wtx = div_up(cols, U8W_TW), wty = div_up(rows, U8W_TH);
+                const size_t wtiles = (size_t)wtx * wty * batch;
+                if (smem_w > 48 * 1024) {
+                    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+                    if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem_w, cudaGetErrorString(e));
+                }
+                kern<<<(unsigned)wtiles, 256, smem_w, s>>>(src, dst, cols, rows, wtx, wty, T);
+                return check_launch("blur_u8_tile_w_kernel");
+            };
+#define KB200_U8W(CC, KK) if (C == CC && T.kxn == KK) return gow(blur_u8_tile_w_kernel<CC, KK>, KK);
+            KB200_U8W(1, 3) KB200_U8W(1, 5) KB200_U8W(1, 7) KB200_U8W(3, 3) KB200_U8W(3, 5) KB200_U8W(3, 7) KB200_U8W(4, 3) KB200_U8W(4, 5) KB200_U8W(4, 7)
+#undef KB200_U8W
+        }
+    }
 #define KB200_U8B(CC)                                                                   \
     if (C == CC) {                                                                      \
         if (T.kxn == T.kyn && T.kxn == 3) return go(blur_u8_tile_kernel<CC, 3>);        \

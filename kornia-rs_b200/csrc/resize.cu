@@ -410,6 +410,12 @@ KB200_API int kb200_resize_fast_u8(kb200_stream_t stream, const uint8_t* src, si
         return check_launch("pyrup_2x_rgb_u8_kernel");
     }
     if (interp == KB200_INTERP_NEAREST) {
+        // exact 3:1: floor((i + 0.5) * 3) = 3i + 1 — the same centre-pixel gather as the bilinear 3:1 case
+        if (C == 3 && sw == 3 * dw && sh == 3 * dh && (dw & 3u) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0) {
+            dim3 wgrid(div_up(dw / 4, 32), div_up(dh, 8), batch);
+            resize_bilinear_u8_c3_3to1_kernel<<<wgrid, block, 0, s>>>(reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst), sw, sh, dw, dh);
+            return check_launch("resize_bilinear_u8_c3_3to1_kernel");
+        }
         const double scale_x = (double)sw / (double)dw, scale_y = (double)sh / (double)dh;
         if (C == 1) resize_nearest_u8_kernel<1><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, C, scale_x, scale_y);
         else if (C == 3) resize_nearest_u8_kernel<3><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, C, scale_x, scale_y);

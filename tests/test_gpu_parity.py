@@ -244,7 +244,7 @@ U8_FAST = [  # (sw, sh, dw, dh, c, mode)  mode: 1 = Bilinear, 0 = Nearest
     (64, 48, 32, 24, 3, 1), (2, 2, 1, 1, 3, 1), (130, 6, 65, 3, 3, 1), (3840, 8, 1920, 4, 3, 1), (72, 10, 36, 5, 3, 1), (1928, 6, 964, 3, 3, 1),   # pyrdown arm (byte and word kernels)
     (2, 2, 4, 4, 3, 1), (3, 4, 6, 8, 3, 1), (17, 9, 34, 18, 3, 1), (33, 6, 66, 12, 3, 1), (640, 5, 1280, 10, 3, 1),   # pyrup arm
     (64, 48, 32, 24, 1, 1), (64, 48, 32, 24, 4, 1), (13, 9, 7, 5, 3, 1), (96, 63, 32, 21, 3, 1), (3840, 9, 1280, 3, 3, 1), (36, 9, 12, 3, 3, 1), (30, 9, 10, 3, 3, 1),                                     # 2x but not RGB / generic → Q14 arm
-    (7, 5, 3, 2, 3, 0), (5, 5, 9, 7, 1, 0), (64, 48, 1, 1, 4, 0), (1, 1, 8, 8, 2, 0), (23, 37, 11, 17, 5, 0), (1920, 9, 640, 3, 3, 0),
+    (7, 5, 3, 2, 3, 0), (5, 5, 9, 7, 1, 0), (64, 48, 1, 1, 4, 0), (1, 1, 8, 8, 2, 0), (23, 37, 11, 17, 5, 0), (1920, 9, 640, 3, 3, 0), (96, 63, 32, 21, 3, 0), (30, 9, 10, 3, 3, 0),
 ]
 
 
