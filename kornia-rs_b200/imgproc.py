@@ -153,11 +153,15 @@ class HostPipeline:
         self.depth = depth
 
     def close(self) -> None:
-        if getattr(self, "_h", None):
-            _lib.lib().kb200_host_pipeline_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.lib().kb200_host_pipeline_destroy(h)
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: the library handle may already be gone
+            pass
 
     def last_transfer(self) -> tuple[int, int]:
         """(h2d_bytes, d2h_bytes) the last call moved over the link."""

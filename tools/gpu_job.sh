@@ -1,19 +1,15 @@
 #!/bin/bash
 # Scratch driver for one gpurun call (edited per experiment; the durable scripts are tools/run_op.py and bench.py).
-python -m pytest tests -m gpu -x -q -k "blur_u8 or box_blur or resize_fast_u8" 2>&1 | tail -3
-python - <<'PY'
-import torch, kornia_rs_b200 as kb
-dev=torch.device("cuda:0")
-n,w,h=16,3840,2160
-src=kb.Image(torch.randint(0,256,(n,h,w,3),dtype=torch.uint8,device=dev))
-dst=kb.Image.zeros_cuda(kb.ImageSize(w,h),3,torch.uint8,dev,batch=n)
-for name,fn in [("gaussian_blur_u8 5x5",lambda: kb.imgproc.gaussian_blur_u8(src,dst,(5,5),(1.5,1.5))),("gaussian_blur_u8 3x3 binomial",lambda: kb.imgproc.gaussian_blur_u8(src,dst,(3,3),(1.0,1.0))),("gaussian_blur_u8 7x7",lambda: kb.imgproc.gaussian_blur_u8(src,dst,(7,7),(2.0,2.0)))]:
-    for _ in range(3): fn()
-    torch.cuda.synchronize()
-    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): fn()
-    e1.record(); torch.cuda.synchronize()
-    ms=e0.elapsed_time(e1)/10
-    print(f"{name} 4K x{n}: {ms:.4f} ms  {n*w*h/1e6/ms*1e3:.0f} Mpix/s  src+dst {(2*n*w*h*3)/ms/1e6:.0f} GB/s")
-PY
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref_r1.json 2>gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref_r1.json
+python bench.py --steps 100 --warmup 10 2>gpurun_out/b.err > gpurun_out/bench_r1.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_r1.json'))
+print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline'].get('frac_of_traffic'), d['e2e']['value'], d['e2e']['ms_per_step'], d['clocks'])
+for k,v in d.get('ops',{}).items(): print(k, v if not isinstance(v,dict) else {a:b for a,b in v.items() if a in ('ms','frac','mpix_s')})
+print(d.get('cpu_baseline'))"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kb200 --kernel-name-base demangled -c 700 --csv \
+  --log-file gpurun_out/launches_r1.csv python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+wc -l gpurun_out/launches_r1.csv
+KB_BATCH=64 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_rows -s 4 -c 1 -o gpurun_out/cfg2_r1d -f python tools/run_op.py cfg2 3 > gpurun_out/cfg2d_ncu.log 2>&1; tail -1 gpurun_out/cfg2d_ncu.log
