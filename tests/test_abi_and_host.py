@@ -283,3 +283,17 @@ def test_resize_row_plan_matches_tapped_rows(kb):
         y1 = np.where(wy == 0, y0, np.minimum(y0 + 1, sh - 1))
         for y in np.concatenate([y0, y1]):
             assert F <= int(y) % P < F + K, (sh, dh, int(y), (P, F, K))
+
+
+def test_ctypes_table_matches_the_header(kb):
+    """Every entry point the header declares has a ctypes signature in _lib.py, and nothing is bound that the header does
+    not declare — the binding the tests exercise is the documented ABI, all of it."""
+    hdr = open(os.path.join(ROOT, "include", "kornia_b200.h")).read()
+    declared = set(re.findall(r"KB200_API\s+[\w\s\*]+?\b(kb200_\w+)\s*\(", hdr))
+    from kornia_rs_b200 import _lib
+
+    bound = set(re.findall(r'"(kb200_\w+)":', open(_lib.__file__).read()))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    lib = _lib.lib()
+    for name in declared:
+        assert getattr(lib, name).argtypes is not None, name
