@@ -1,15 +1,4 @@
 #!/bin/bash
 # Scratch driver for one gpurun call (edited per experiment; the durable scripts are tools/run_op.py and bench.py).
-mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
-python bench.py --impl reference --steps 10 --warmup 3 > gpurun_out/bench_ref_r1.json 2>gpurun_out/bench_ref.err; cut -c1-200 gpurun_out/bench_ref_r1.json
-python bench.py --steps 100 --warmup 10 2>gpurun_out/b.err > gpurun_out/bench_r1.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1.json'))
-print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline'].get('frac_of_traffic'), d['e2e']['value'], d['e2e']['ms_per_step'], d['clocks'])
-for k,v in d.get('ops',{}).items(): print(k, v if not isinstance(v,dict) else {a:b for a,b in v.items() if a in ('ms','frac','mpix_s')})
-print(d.get('cpu_baseline'))"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:kb200 --kernel-name-base demangled -c 700 --csv \
-  --log-file gpurun_out/launches_r1.csv python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-wc -l gpurun_out/launches_r1.csv
-KB_BATCH=64 timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_rows -s 4 -c 1 -o gpurun_out/cfg2_r1d -f python tools/run_op.py cfg2 3 > gpurun_out/cfg2d_ncu.log 2>&1; tail -1 gpurun_out/cfg2d_ncu.log
+python -m pytest tests -m gpu -x -q -k "warp and not u8" 2>&1 | tail -1
+for pf in 96 128 160 192; do echo -n "pf=$pf "; KB200_WARP_PF=$pf python tools/run_op.py warp 30; done
