@@ -82,6 +82,8 @@ pub mod ffi {
                                         src_h: u32, dst_w: u32, dst_h: u32, channels: u32, batch: u32) -> c_int;
         pub fn kb200_resize_fast_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32, src_h: u32,
                                     dst_w: u32, dst_h: u32, channels: u32, batch: u32, interp: c_int) -> c_int;
+        pub fn kb200_yuyv_from_rgb_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, width: u32, height: u32, batch: u32) -> c_int;
+        pub fn kb200_nv12_from_rgb_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, width: u32, height: u32, batch: u32) -> c_int;
         pub fn kb200_warp_affine_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32, src_h: u32,
                                     dst_w: u32, dst_h: u32, channels: u32, batch: u32, m: *const f32) -> c_int;
         pub fn kb200_warp_perspective_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32,

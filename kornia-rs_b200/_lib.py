@@ -63,6 +63,8 @@ def _declare(l: C.CDLL) -> None:
         "kb200_box_blur_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32], i),
         "kb200_remap_f32_c3": ([vp, vp, sz, vp, sz, vp, vp, sz, u32, u32, u32, u32, u32, i], i),
         "kb200_remap_u8": ([vp, vp, sz, vp, sz, vp, vp, sz, u32, u32, u32, u32, u32, u32, i], i),
+        "kb200_yuyv_from_rgb_u8": ([vp, vp, sz, vp, sz, u32, u32, u32], i),
+        "kb200_nv12_from_rgb_u8": ([vp, vp, sz, vp, sz, u32, u32, u32], i),
         "kb200_warp_affine_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, fp], i),
         "kb200_warp_perspective_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, u32, fp], i),
         "kb200_invert_affine_transform": ([fp, fp], None),

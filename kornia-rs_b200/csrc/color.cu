@@ -257,6 +257,47 @@ static inline unsigned stream_grid(size_t items, unsigned block, unsigned ctas_p
     return (unsigned)std::max<size_t>(1, std::min(want, cap));
 }
 
+// ── RGB8 → YUYV / NV12 encode ─────────────────────────────────────────────
+// color/yuv/kernels.rs:1223-1252: Q8 BT.601 limited — Y = ((66R + 129G + 25B + 128) >> 8) + 16,
+// U = ((-38R - 74G + 112B + 128) >> 8) + 128, V = ((112R - 94G - 18B + 128) >> 8) + 128, clamped to 0..255.
+__device__ __forceinline__ uint32_t enc_y(int r, int g, int b) { return (uint32_t)min(max(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16, 0), 255); }
+__device__ __forceinline__ uint32_t enc_u(int r, int g, int b) { return (uint32_t)min(max(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128, 0), 255); }
+__device__ __forceinline__ uint32_t enc_v(int r, int g, int b) { return (uint32_t)min(max(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128, 0), 255); }
+
+// One thread per pixel pair: 6 bytes in, one 32-bit word `Y0 U Y1 V` out (lane-contiguous stores).  kernels.rs:1301-1322.
+__global__ void __launch_bounds__(256) yuyv_from_rgb_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, size_t npairs) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < npairs; g += stride) {
+        const uint8_t* s = src + g * 6;
+        const int r0 = s[0], g0 = s[1], b0 = s[2], r1 = s[3], g1 = s[4], b1 = s[5];
+        const int ra = (r0 + r1 + 1) >> 1, ga = (g0 + g1 + 1) >> 1, ba = (b0 + b1 + 1) >> 1;   // shared chroma: rounded pair average
+        const uint32_t w = enc_y(r0, g0, b0) | (enc_u(ra, ga, ba) << 8) | (enc_y(r1, g1, b1) << 16) | (enc_v(ra, ga, ba) << 24);
+        uint8_t* d = dst + g * 4;
+        if ((reinterpret_cast<uintptr_t>(d) & 3u) == 0) *reinterpret_cast<uint32_t*>(d) = w;
+        else { d[0] = (uint8_t)w; d[1] = (uint8_t)(w >> 8); d[2] = (uint8_t)(w >> 16); d[3] = (uint8_t)(w >> 24); }
+    }
+}
+
+// One thread per 2x2 block: 4 luma bytes (two 16-bit stores) + one UV pair.  kernels.rs:1480-1516, :1563-1576.
+__global__ void __launch_bounds__(256) nv12_from_rgb_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, uint32_t width,
+                                                            uint32_t height, size_t frame_bytes) {
+    const uint32_t cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (cx >= width / 2 || cy >= height / 2) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * width * height * 3;
+    uint8_t* frame = dst + (size_t)blockIdx.z * frame_bytes;
+    const uint8_t* t = s + ((size_t)(2 * cy) * width + 2 * cx) * 3;
+    const uint8_t* b = t + (size_t)width * 3;
+    const int r00 = t[0], g00 = t[1], b00 = t[2], r01 = t[3], g01 = t[4], b01 = t[5];
+    const int r10 = b[0], g10 = b[1], b10 = b[2], r11 = b[3], g11 = b[4], b11 = b[5];
+    uint8_t* y0 = frame + (size_t)(2 * cy) * width + 2 * cx;
+    uint8_t* y1 = y0 + width;
+    y0[0] = (uint8_t)enc_y(r00, g00, b00); y0[1] = (uint8_t)enc_y(r01, g01, b01);
+    y1[0] = (uint8_t)enc_y(r10, g10, b10); y1[1] = (uint8_t)enc_y(r11, g11, b11);
+    const int ra = (r00 + r01 + r10 + r11 + 2) >> 2, ga = (g00 + g01 + g10 + g11 + 2) >> 2, ba = (b00 + b01 + b10 + b11 + 2) >> 2;
+    uint8_t* uv = frame + (size_t)width * height + (size_t)cy * width + 2 * cx;
+    uv[0] = (uint8_t)enc_u(ra, ga, ba); uv[1] = (uint8_t)enc_v(ra, ga, ba);
+}
+
 }  // namespace kb200
 
 using namespace kb200;
@@ -357,6 +398,32 @@ KB200_API int kb200_rgb_from_yuyv_u8(kb200_stream_t stream, const uint8_t* src, 
         KB200_TRY(check_launch("rgb_from_yuyv_generic"));
     }
     return KB200_OK;
+}
+
+
+KB200_API int kb200_yuyv_from_rgb_u8(kb200_stream_t stream, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len,
+                                     uint32_t width, uint32_t height, uint32_t batch) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_geometry(width, height, width, height, batch));
+    if (width & 1u) return fail(KB200_ERR_INVALID_ARGUMENT, "YUYV needs an even width, got %u", width);   // color/yuv/mod.rs:282-284
+    const size_t npx = (size_t)width * height * batch;
+    KB200_TRY(check_slice("src", src_len, npx * 3)); KB200_TRY(check_slice("dst", dst_len, npx * 2));
+    const size_t npairs = npx / 2;
+    yuyv_from_rgb_kernel<<<stream_grid(npairs, 256, 16), 256, 0, as_stream(stream)>>>(src, dst, npairs);
+    return check_launch("yuyv_from_rgb_kernel");
+}
+
+KB200_API int kb200_nv12_from_rgb_u8(kb200_stream_t stream, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len,
+                                     uint32_t width, uint32_t height, uint32_t batch) {
+    KB200_TRY(check_ptr("src", src)); KB200_TRY(check_ptr("dst", dst));
+    KB200_TRY(check_geometry(width, height, width, height, batch));
+    if ((width & 1u) || (height & 1u)) return fail(KB200_ERR_INVALID_ARGUMENT, "NV12 needs even dimensions, got %ux%u", width, height);   // color/yuv/mod.rs:298-300
+    if (batch > 65535u) return fail(KB200_ERR_INVALID_ARGUMENT, "batch %u exceeds 65535 per call", batch);
+    const size_t frame = (size_t)width * height * 3 / 2;
+    KB200_TRY(check_slice("src", src_len, (size_t)width * height * 3 * batch)); KB200_TRY(check_slice("dst", dst_len, frame * batch));
+    dim3 block(32, 8), grid(div_up(width / 2, 32), div_up(height / 2, 8), batch);
+    nv12_from_rgb_kernel<<<grid, block, 0, as_stream(stream)>>>(src, dst, width, height, frame);
+    return check_launch("nv12_from_rgb_kernel");
 }
 
 }  // extern "C"

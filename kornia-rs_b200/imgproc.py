@@ -519,6 +519,36 @@ def rgb_from_yuyv(src, dst: Image) -> None:
     _check(_lib.lib().kb200_rgb_from_yuyv_u8(_stream(t.device), t.data_ptr(), t.numel(), dst.data.data_ptr(), dst.numel(), w, h, n))
 
 
+def _encode(op: str, fn_name: str, src: Image, dst: torch.Tensor, bytes_per_px_num: int, bytes_per_px_den: int, need_even_h: bool) -> None:
+    if not src.is_device:
+        raise ImageError.HostPathNotBuilt(op)
+    _expect_dtype(src, torch.uint8, "src")
+    if src.num_channels() != 3:
+        raise ImageError.UnsupportedChannelCount(src.num_channels())
+    if not isinstance(dst, torch.Tensor) or not dst.is_cuda:
+        raise ImageError.MixedResidency()
+    if dst.device != src.data.device:
+        raise ImageError.DeviceMismatch()
+    if dst.dtype != torch.uint8 or not dst.is_contiguous():
+        raise ImageError.DtypeMismatch(torch.uint8, dst.dtype)
+    w, h, n = src.cols(), src.rows(), src.batch
+    need = w * h * bytes_per_px_num // bytes_per_px_den * n
+    if w % 2 != 0 or (need_even_h and h % 2 != 0) or dst.numel() != need:   # color/yuv/mod.rs:282-284, :298-300
+        raise ImageError.InvalidImageSize(dst.numel(), w, h, need)
+    _lib.set_device(dst.device.index)
+    _check(getattr(_lib.lib(), fn_name)(_stream(dst.device), src.data.data_ptr(), src.numel(), dst.data_ptr(), dst.numel(), w, h, n))
+
+
+def yuyv_from_rgb(src: Image, dst: torch.Tensor) -> None:
+    """color/yuv/mod.rs:280 — RGB8 → packed YUYV (`Y0 U Y1 V`, BT.601 limited); `dst`: u8, width*height*2 bytes per image."""
+    _encode("yuyv_from_rgb", "kb200_yuyv_from_rgb_u8", src, dst, 2, 1, False)
+
+
+def nv12_from_rgb(src: Image, dst: torch.Tensor) -> None:
+    """color/yuv/mod.rs:296 — RGB8 → NV12 (Y plane + interleaved UV); `dst`: u8, width*height*3/2 bytes per image."""
+    _encode("nv12_from_rgb", "kb200_nv12_from_rgb_u8", src, dst, 3, 2, True)
+
+
 # ── normalize / statistics ───────────────────────────────────────────────────
 def normalize_mean_std(src: Image, dst: Image, mean: Sequence[float], std: Sequence[float]) -> None:
     """normalize.rs:56 — (x - mean[c]) / std[c], true division."""

@@ -969,6 +969,43 @@ KO_API int ko_gaussian_blur_f32(const float* src, float* dst, size_t rows, size_
 }
 
 // ─────────────────────────────────────────────────────────────────────────────
+// §8(f)#4 — video ENCODE: color/yuv/kernels.rs:1223-1252 (Q8 BT.601 limited coefficients, encode_y / encode_uv),
+// :1301-1322 (YUYV: luma per pixel, chroma of the rounded pair average), :1480-1516 + :1563-1576 (NV12: luma per pixel,
+// chroma of the rounded 2x2 mean).
+// ─────────────────────────────────────────────────────────────────────────────
+static inline uint8_t enc_y(int r, int g, int b) { return (uint8_t)std::min(std::max(((66 * r + 129 * g + 25 * b + 128) >> 8) + 16, 0), 255); }
+static inline void enc_uv(int r, int g, int b, uint8_t* u, uint8_t* v) {
+    *u = (uint8_t)std::min(std::max(((-38 * r - 74 * g + 112 * b + 128) >> 8) + 128, 0), 255);
+    *v = (uint8_t)std::min(std::max(((112 * r - 94 * g - 18 * b + 128) >> 8) + 128, 0), 255);
+}
+KO_API int ko_yuyv_from_rgb_u8(const uint8_t* src, size_t w, size_t h, uint8_t* dst) {
+    if (w % 2 != 0) return -1;
+    for (size_t row = 0; row < h; ++row)
+        for (size_t g = 0; g < w / 2; ++g) {
+            const uint8_t* s = src + row * w * 3 + g * 6;
+            uint8_t* d = dst + row * w * 2 + g * 4;
+            d[0] = enc_y(s[0], s[1], s[2]); d[2] = enc_y(s[3], s[4], s[5]);
+            enc_uv((s[0] + s[3] + 1) >> 1, (s[1] + s[4] + 1) >> 1, (s[2] + s[5] + 1) >> 1, &d[1], &d[3]);
+        }
+    return 0;
+}
+KO_API int ko_nv12_from_rgb_u8(const uint8_t* src, size_t w, size_t h, uint8_t* dst) {
+    if (w % 2 != 0 || h % 2 != 0) return -1;
+    uint8_t* yp = dst;
+    uint8_t* uv = dst + w * h;
+    for (size_t y = 0; y < h; ++y)
+        for (size_t x = 0; x < w; ++x) { const uint8_t* s = src + (y * w + x) * 3; yp[y * w + x] = enc_y(s[0], s[1], s[2]); }
+    for (size_t cy = 0; cy < h / 2; ++cy)
+        for (size_t cx = 0; cx < w / 2; ++cx) {
+            const uint8_t* t = src + ((2 * cy) * w + 2 * cx) * 3;
+            const uint8_t* b = t + w * 3;
+            enc_uv((t[0] + t[3] + b[0] + b[3] + 2) >> 2, (t[1] + t[4] + b[1] + b[4] + 2) >> 2, (t[2] + t[5] + b[2] + b[5] + 2) >> 2,
+                   &uv[cy * w + 2 * cx], &uv[cy * w + 2 * cx + 1]);
+        }
+    return 0;
+}
+
+// ─────────────────────────────────────────────────────────────────────────────
 // §8(f)#1 — u8 blurs: filter/ops.rs:22-29 (path selection), :59-98 (box_blur_u8), :639-757 (gaussian_blur_u8),
 // :759-770 (quantize_kernel_256), :773-851 + :852-1100 (general Q8 two-pass, replicate border, u8 intermediate),
 // :1105-1285 ([1,2,1]/4 binomial path as nested rounding half-adds).

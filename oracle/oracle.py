@@ -76,6 +76,10 @@ def _declare(l: C.CDLL) -> None:
     l.ko_remap_f32.restype = C.c_int
     l.ko_remap_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp, vp, C.c_int]
     l.ko_remap_u8.restype = C.c_int
+    l.ko_yuyv_from_rgb_u8.argtypes = [vp, sz, sz, vp]
+    l.ko_yuyv_from_rgb_u8.restype = C.c_int
+    l.ko_nv12_from_rgb_u8.argtypes = [vp, sz, sz, vp]
+    l.ko_nv12_from_rgb_u8.restype = C.c_int
     l.ko_warp_affine_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
     l.ko_warp_affine_u8.restype = C.c_int
     l.ko_warp_perspective_u8.argtypes = [vp, sz, sz, vp, sz, sz, sz, vp]
@@ -512,4 +516,25 @@ def remap(src: np.ndarray, map_x: np.ndarray, map_y: np.ndarray, mode: int = 1) 
         rc = lib().ko_remap_f32(_p(src), sw, sh, _p(dst), dw, dh, c, _p(mx), _p(my), mode)
     if rc != 0:
         raise ValueError("UnsupportedInterpolation")
+    return dst
+
+
+# ── video encode ───────────────────────────────────────────
+def yuyv_from_rgb(src: np.ndarray) -> np.ndarray:
+    """color/yuv/mod.rs:280 — RGB8 -> packed YUYV (BT.601 limited, Q8); flat w*h*2 bytes."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w, _ = src.shape
+    dst = np.zeros(w * h * 2, np.uint8)
+    if lib().ko_yuyv_from_rgb_u8(_p(src), w, h, _p(dst)) != 0:
+        raise ValueError("InvalidImageSize")
+    return dst
+
+
+def nv12_from_rgb(src: np.ndarray) -> np.ndarray:
+    """color/yuv/mod.rs:296 — RGB8 -> NV12 (Y plane + interleaved UV); flat w*h*3/2 bytes."""
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w, _ = src.shape
+    dst = np.zeros(w * h * 3 // 2, np.uint8)
+    if lib().ko_nv12_from_rgb_u8(_p(src), w, h, _p(dst)) != 0:
+        raise ValueError("InvalidImageSize")
     return dst

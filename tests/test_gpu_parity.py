@@ -888,3 +888,22 @@ def test_entry_points_are_cuda_graph_capturable(kb, oracle, dev):
         side.synchronize()
     for got, ref in zip((fused, blur.data, edge.data, warped.data, u8w.data), want):
         assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("w,h", [(8, 6), (34, 18), (1920, 22), (130, 4)])
+def test_video_encode(kb, oracle, dev, w, h):
+    """yuyv_from_rgb / nv12_from_rgb (Q8 BT.601 limited) — bit-exact, batched; and decode(encode(x)) runs end to end."""
+    n = 3
+    src = np.stack([oracle.pattern_u8(w * h * 3, 0x5150 + i).reshape(h, w, 3) for i in range(n)])
+    img = kb.Image(cu(src, dev))
+    yuyv = torch.full((n, w * h * 2), 0xCD, dtype=torch.uint8, device=dev)
+    kb.imgproc.yuyv_from_rgb(img, yuyv)
+    np.testing.assert_array_equal(yuyv.cpu().numpy(), np.stack([oracle.yuyv_from_rgb(src[i]) for i in range(n)]))
+    nv12 = torch.full((n, w * h * 3 // 2), 0xCD, dtype=torch.uint8, device=dev)
+    kb.imgproc.nv12_from_rgb(img, nv12)
+    np.testing.assert_array_equal(nv12.cpu().numpy(), np.stack([oracle.nv12_from_rgb(src[i]) for i in range(n)]))
+    back = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.uint8, dev, batch=n)
+    kb.imgproc.rgb_from_nv12(nv12, back)
+    np.testing.assert_array_equal(back.numpy(), np.stack([oracle.rgb_from_nv12(oracle.nv12_from_rgb(src[i]), w, h) for i in range(n)]))
+    with pytest.raises(kb.ImageError, match="Invalid image size"):
+        kb.imgproc.nv12_from_rgb(img, torch.zeros(7, dtype=torch.uint8, device=dev))

@@ -762,3 +762,38 @@ def test_remap_equals_warp_for_an_affine_map(oracle):
     mx = ((inv[1] * y + inv[2]) + inv[0] * x) * inv_nd
     my = ((inv[4] * y + inv[5]) + inv[3] * x) * inv_nd
     np.testing.assert_array_equal(oracle.remap(src, mx, my, 1), oracle.warp_perspective_u8(src, 40, 30, H))
+
+
+# ── §8(f)#4: video encode ─────────────────────────────────────────────────────
+def test_video_encode_reference_known_answers(oracle):
+    """color/yuv/kernels.rs:1890-1925 (constant colour survives encode -> decode within 2 LSB, YUYV and NV12),
+    :1927-1950 (YUYV layout `Y0 U Y1 V`, chroma from the rounded pair average) and an independent numpy restatement
+    of the Q8 formulas (:1223-1252)."""
+    w, h = 8, 6
+    for (r, g, b) in [(200, 50, 25), (0, 0, 0), (255, 255, 255), (17, 200, 99)]:
+        rgb = np.tile(np.array([r, g, b], np.uint8), (h, w, 1))
+        back = oracle.rgb_from_yuyv(oracle.yuyv_from_rgb(rgb), w, h)
+        assert int(np.abs(back.astype(int) - rgb.astype(int)).max()) <= 2
+        back = oracle.rgb_from_nv12(oracle.nv12_from_rgb(rgb), w, h)
+        assert int(np.abs(back.astype(int) - rgb.astype(int)).max()) <= 2
+    ey = lambda R, G, B: np.clip(((66 * R + 129 * G + 25 * B + 128) >> 8) + 16, 0, 255)
+    eu = lambda R, G, B: np.clip(((-38 * R - 74 * G + 112 * B + 128) >> 8) + 128, 0, 255)
+    ev = lambda R, G, B: np.clip(((112 * R - 94 * G - 18 * B + 128) >> 8) + 128, 0, 255)
+    out = oracle.yuyv_from_rgb(np.array([[[255, 0, 0], [0, 0, 255]]], np.uint8))
+    assert list(out) == [ey(255, 0, 0), eu(128, 0, 128), ey(0, 0, 255), ev(128, 0, 128)]
+    img = oracle.pattern_u8(34 * 18 * 3, 21).reshape(18, 34, 3).astype(np.int64)
+    R, G, B = img[..., 0], img[..., 1], img[..., 2]
+    yuyv = oracle.yuyv_from_rgb(img.astype(np.uint8)).reshape(18, 17, 4)
+    np.testing.assert_array_equal(yuyv[..., 0], ey(R[:, 0::2], G[:, 0::2], B[:, 0::2]))
+    np.testing.assert_array_equal(yuyv[..., 2], ey(R[:, 1::2], G[:, 1::2], B[:, 1::2]))
+    pa = lambda c: (c[:, 0::2] + c[:, 1::2] + 1) >> 1
+    np.testing.assert_array_equal(yuyv[..., 1], eu(pa(R), pa(G), pa(B)))
+    np.testing.assert_array_equal(yuyv[..., 3], ev(pa(R), pa(G), pa(B)))
+    nv = oracle.nv12_from_rgb(img.astype(np.uint8))
+    np.testing.assert_array_equal(nv[:34 * 18].reshape(18, 34), ey(R, G, B))
+    qa = lambda c: (c[0::2, 0::2] + c[0::2, 1::2] + c[1::2, 0::2] + c[1::2, 1::2] + 2) >> 2
+    uv = nv[34 * 18:].reshape(9, 17, 2)
+    np.testing.assert_array_equal(uv[..., 0], eu(qa(R), qa(G), qa(B)))
+    np.testing.assert_array_equal(uv[..., 1], ev(qa(R), qa(G), qa(B)))
+    with pytest.raises(ValueError):
+        oracle.nv12_from_rgb(np.zeros((5, 4, 3), np.uint8))
