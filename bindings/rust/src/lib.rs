@@ -19,14 +19,15 @@ use cudarc::driver::{CudaContext, CudaSlice, CudaStream, DevicePtr, DevicePtrMut
 pub mod ffi {
     use super::*;
 
-    #[repr(C)]
-    #[derive(Clone, Copy, Debug, Default)]
     /// Opaque staging ring of the host-buffer entry points (include/kornia_b200.h, kb200_host_pipeline).
     #[repr(C)]
     pub struct kb200_host_pipeline {
         _private: [u8; 0],
     }
 
+    /// include/kornia_b200.h `kb200_preprocess_desc` — 20 four-byte fields, 80 bytes, C layout.
+    #[repr(C)]
+    #[derive(Clone, Copy, Debug, Default)]
     pub struct kb200_preprocess_desc {
         pub scale_x: f32,
         pub scale_y: f32,
@@ -45,8 +46,12 @@ pub mod ffi {
         pub sampling: i32,
     }
 
+    const _: () = assert!(std::mem::size_of::<kb200_preprocess_desc>() == 80);
+
     extern "C" {
         pub fn kb200_version() -> c_int;
+        pub fn kb200_last_kernel() -> *const c_char;
+        pub fn kb200_debug_set_knob(name: *const c_char, value: c_int) -> c_int;
         pub fn kb200_last_error() -> *const c_char;
         pub fn kb200_status_name(status: c_int) -> *const c_char;
         pub fn kb200_set_device(ordinal: c_int) -> c_int;

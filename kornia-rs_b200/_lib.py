@@ -39,6 +39,8 @@ def _declare(l: C.CDLL) -> None:
         "kb200_version": ([], i),
         "kb200_last_error": ([], C.c_char_p),
         "kb200_status_name": ([i], C.c_char_p),
+        "kb200_last_kernel": ([], C.c_char_p),
+        "kb200_debug_set_knob": ([C.c_char_p, i], i),
         "kb200_set_device": ([i], i),
         "kb200_device_info": ([C.POINTER(i)] * 3, i),
         "kb200_resize_bilinear_f32_c3": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, i], i),
@@ -116,6 +118,17 @@ def lib() -> C.CDLL:
 
 def last_error() -> str:
     return lib().kb200_last_error().decode("utf-8", "replace")
+
+
+def last_kernel() -> str:
+    """Name of the kernel the calling thread's last launcher call enqueued."""
+    return lib().kb200_last_kernel().decode("utf-8", "replace")
+
+
+def set_knob(name: str, value: int) -> None:
+    st = lib().kb200_debug_set_knob(name.encode(), int(value))
+    if st != OK:
+        raise ValueError(last_error())
 
 
 def set_device(ordinal: int) -> None:

@@ -436,18 +436,13 @@ __global__ void __launch_bounds__(SS2<NV>::THREADS) sep_filter_stream2_kernel(co
     }
 }
 
-static int ss_env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 template <int C, int KX, int KY, bool SOBEL, int NV>
 static int launch_sep_stream2(cudaStream_t s, const float* src, float* dst, const SepTaps& taps, uint32_t cols, uint32_t rows,
                               uint32_t batch) {
     using G = SS2<NV>;
     constexpr int HX = KX / 2;
     constexpr int HL = ((HX * C + 3) / 4) * 4, HR = (((KX - 1 - HX) * C + 3) / 4) * 4;
-    static const int tune_stages = ss_env_int("KB200_SS_STAGES", 0), tune_ctas = ss_env_int("KB200_SS_CTAS", 0);
+    const int tune_stages = knob(KNOB_SS_STAGES), tune_ctas = knob(KNOB_SS_CTAS);   // developer sweeps only (kb200_debug_set_knob)
     SepStream2Params R;
     SepStreamParams& P = R.g;
     P.rowlen = cols * C; P.rows = rows; P.batch = batch;
@@ -468,13 +463,11 @@ static int launch_sep_stream2(cudaStream_t s, const float* src, float* dst, cons
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, G::THREADS, smem);
         if (e != cudaSuccess || resident < 1) return fail(KB200_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
     }
-    static const bool debug = ss_env_int("KB200_SS_DEBUG", 0) != 0;
-    if (debug) fprintf(stderr, "[kb200] sep_stream2 C=%d K=%d sobel=%d NV=%d: stages=%u smem=%zu per_sm=%d resident=%d\n", C, KX, (int)SOBEL, NV, stages, smem, per_sm, resident);
     const size_t ctas = (size_t)device_info().sm_count * std::min(per_sm, resident);
     // chunk height: ~12 units per CTA keeps the persistent grid balanced (a search that traded balance against the
     // KY-1 halo rows per chunk measured 8-13 % slower on B200: long chunks leave the ragged last strip's CTAs idle);
     // at least 32 rows so the halo re-reads stay near 10 %
-    static const int tune_rc = ss_env_int("KB200_SS_RC", 0);
+    const int tune_rc = knob(KNOB_SS_RC);
     const size_t total = (size_t)P.strips * batch * rows;
     uint32_t rc = tune_rc > 0 ? (uint32_t)tune_rc : (uint32_t)std::max<size_t>(32, total / (ctas * 12));
     rc = std::min(rc, rows);

@@ -2,6 +2,7 @@
 // (matrix inversion, Gaussian taps, preprocess geometry, std_mean finalisation).
 // Host arithmetic mirrors the reference's f32/f64 expression trees; this file is compiled by
 // nvcc with -fmad=false and the host compiler flags -ffp-contract=off (see build()).
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -25,7 +26,19 @@ int fail(int status, const char* fmt, ...) {
     return status;
 }
 
+static const char*& last_kernel_ref() {
+    static thread_local const char* s = "";
+    return s;
+}
+
+static std::atomic<int> g_knobs[KNOB_COUNT];
+static const char* const g_knob_names[KNOB_COUNT] = {
+    "fr.npx", "fr.stages", "fr.ctas", "ss.stages", "ss.ctas", "ss.rc", "warp.pf", "warp.path",
+    "ws.stages", "ws.ctas", "ws.rc", "ws.npx", "rs.stages", "rs.ctas", "rs.npx", "a", "b", "c", "d"};
+int knob(Knob k) { return g_knobs[k].load(std::memory_order_relaxed); }
+
 int check_launch(const char* what) {
+    last_kernel_ref() = what;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "CUDA launch of %s failed: %s", what, cudaGetErrorString(e));
     return KB200_OK;
@@ -73,6 +86,15 @@ KB200_API const char* kb200_status_name(int st) {
         case KB200_ERR_INVALID_SOURCE: return "KB200_ERR_INVALID_SOURCE";
         default: return "KB200_ERR_UNKNOWN";
     }
+}
+
+KB200_API const char* kb200_last_kernel(void) { return last_kernel_ref(); }
+
+KB200_API int kb200_debug_set_knob(const char* name, int value) {
+    if (!name) return fail(KB200_ERR_INVALID_ARGUMENT, "null knob name");
+    for (int k = 0; k < KNOB_COUNT; ++k)
+        if (strcmp(name, g_knob_names[k]) == 0) { g_knobs[k].store(value, std::memory_order_relaxed); return KB200_OK; }
+    return fail(KB200_ERR_INVALID_ARGUMENT, "unknown knob '%s'", name);
 }
 
 KB200_API int kb200_set_device(int ordinal) {

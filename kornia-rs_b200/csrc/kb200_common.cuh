@@ -23,7 +23,20 @@ namespace kb200 {
 // ── error model ─────────────────────────────────────────────────────────────────────────────
 std::string& last_error_ref();
 int fail(int status, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
-int check_launch(const char* what);  // cudaGetLastError() -> KB200_ERR_CUDA
+int check_launch(const char* what);  // cudaGetLastError() -> KB200_ERR_CUDA; records `what` for kb200_last_kernel()
+
+// Developer tuning knobs (kb200_debug_set_knob): process-wide integers the launchers consult instead of the
+// environment.  0 = "use the built-in choice".  Product code never needs them; sweeps and tests do.
+enum Knob {
+    KNOB_FR_NPX = 0, KNOB_FR_STAGES, KNOB_FR_CTAS,          // fused_rows (resize_fused.cu)
+    KNOB_SS_STAGES, KNOB_SS_CTAS, KNOB_SS_RC,               // sep_filter_stream2 (filter.cu)
+    KNOB_WARP_PF, KNOB_WARP_PATH,                           // warp.cu: prefetch rows (-1 = off); forced path (1 gather, 2 tiled, 3 stream)
+    KNOB_WS_STAGES, KNOB_WS_CTAS, KNOB_WS_RC, KNOB_WS_NPX,  // warp_stream
+    KNOB_RS_STAGES, KNOB_RS_CTAS, KNOB_RS_NPX,              // resize_rows_f32
+    KNOB_A, KNOB_B, KNOB_C, KNOB_D,                         // scratch knobs for experiments
+    KNOB_COUNT
+};
+int knob(Knob k);
 
 // SliceTooSmall{what,got,need} — cuda/mod.rs:104-126
 inline int check_slice(const char* what, size_t got, size_t need) {

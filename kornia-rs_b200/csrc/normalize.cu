@@ -131,9 +131,15 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ s
     }
 }
 
-__global__ void minmax_finish_kernel(uint32_t* mm) {
+// The reference seeds min and max with the FIRST element (normalize.rs:128-134): a NaN first element never loses a
+// comparison, so the result is (NaN, NaN) — reproduced here.  NaNs elsewhere never win (same as the reference).
+// Ties between -0.0 and +0.0 resolve to -0.0 for min / +0.0 for max (bit-pattern order) instead of first occurrence;
+// the two are numerically equal and normalize_min_max differs only in the sign of an exact zero.
+__global__ void minmax_finish_kernel(uint32_t* mm, const float* __restrict__ src) {
     float* f = reinterpret_cast<float*>(mm);
-    const float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+    const float first = src[0];
+    float lo = ord2f(mm[0]), hi = ord2f(mm[1]);
+    if (first != first) { lo = first; hi = first; }
     f[0] = lo; f[1] = hi;
 }
 
@@ -153,15 +159,17 @@ __global__ void __launch_bounds__(256) normalize_min_max_kernel(const float* __r
 // vector q is element 16q + j = channel (q + j) % 3; the grid stride is a multiple of 3, so a thread accumulates
 // into three phase-RELATIVE accumulators and rotates them to absolute channels once at the end.  Per-thread u32
 // accumulators are flushed into u64 before they can overflow (255² * 6 bytes * 8192 vectors < 2^32).
-__global__ void __launch_bounds__(256) std_mean_kernel(const uint8_t* __restrict__ src, size_t nbytes, size_t nvec,
+// `head` = leading bytes (0..15) in front of the first 16-byte-aligned address: they and the tail are summed byte-wise
+// by one thread; the vector body starts at src + head, which rotates the channel phase by head % 3.
+__global__ void __launch_bounds__(256) std_mean_kernel(const uint8_t* __restrict__ src, size_t nbytes, uint32_t head, size_t nvec,
                                                        unsigned long long* __restrict__ sums) {
     unsigned long long s64[3] = {0, 0, 0}, q64[3] = {0, 0, 0};  // phase-relative
     uint32_t s32[3] = {0, 0, 0}, q32[3] = {0, 0, 0};
     const size_t stride = (size_t)gridDim.x * blockDim.x;  // multiple of 3 (launcher)
     size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t ph = (uint32_t)(q % 3);
+    const uint32_t ph = (uint32_t)((q + head) % 3);
     uint32_t pending = 0;
-    const uint4* v4 = reinterpret_cast<const uint4*>(src);
+    const uint4* v4 = reinterpret_cast<const uint4*>(src + head);
     // byte j of word kk is relative channel (kk + j) % 3.  DP4A does the byte sums: Σ b·sel for the plain sums,
     // Σ b·(b & mask) for the squares — 3 LOP + 6 IDP4A per word instead of ~20 scalar ops.
     auto accumulate = [&](const uint4& v) {
@@ -207,13 +215,15 @@ __global__ void __launch_bounds__(256) std_mean_kernel(const uint8_t* __restrict
         sa[c] = r == 0 ? s64[0] : (r == 1 ? s64[1] : s64[2]);
         qa[c] = r == 0 ? q64[0] : (r == 1 ? q64[1] : q64[2]);
     }
-    // tail bytes (nbytes % 16) — thread 0 of CTA 0
+    // head (< 16) and tail (< 16) bytes — thread 0 of CTA 0
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (size_t e = nvec * 16; e < nbytes; ++e) {
+        auto add_byte = [&](size_t e) {
             const uint32_t b = src[e];
             const uint32_t c = (uint32_t)(e % 3);
             if (c == 0) { sa[0] += b; qa[0] += b * b; } else if (c == 1) { sa[1] += b; qa[1] += b * b; } else { sa[2] += b; qa[2] += b * b; }
-        }
+        };
+        for (size_t e = 0; e < head && e < nbytes; ++e) add_byte(e);
+        for (size_t e = (size_t)head + nvec * 16; e < nbytes; ++e) add_byte(e);
     }
     __shared__ unsigned long long red[6][8];
 #pragma unroll
@@ -319,7 +329,7 @@ KB200_API int kb200_find_min_max_f32(kb200_stream_t stream, const float* src, si
     uint32_t* mm = reinterpret_cast<uint32_t*>(minmax_dev);
     minmax_init_kernel<<<1, 1, 0, s>>>(mm);
     minmax_kernel<<<stream_grid(n, 256, 8), 256, 0, s>>>(src, n, mm);
-    minmax_finish_kernel<<<1, 1, 0, s>>>(mm);
+    minmax_finish_kernel<<<1, 1, 0, s>>>(mm, src);
     return check_launch("minmax_kernel");
 }
 
@@ -338,14 +348,10 @@ KB200_API int kb200_std_mean_u8_c3(kb200_stream_t stream, const uint8_t* src, si
     if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
     if (npixels == 0) return KB200_OK;
     const size_t nbytes = npixels * 3;
-    if (aligned16(src)) {
-        const size_t nvec = nbytes / 16;
-        std_mean_kernel<<<stream_grid3(std::max<size_t>(nvec, 1), 256, 6), 256, 0, s>>>(src, nbytes, nvec, reinterpret_cast<unsigned long long*>(sums_dev));
-    } else {
-        // unaligned base: peel leading bytes so the vector body is aligned — done by treating the first (16 - a) bytes
-        // as part of the "tail" is not possible with the phase logic, so fall back to the byte path for everything
-        std_mean_kernel<<<3, 256, 0, s>>>(src, nbytes, 0, reinterpret_cast<unsigned long long*>(sums_dev));
-    }
+    // an unaligned base (a tensor slice) peels up to 15 leading bytes; the vector body then runs on the aligned remainder
+    const uint32_t head = (uint32_t)((16u - (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u);
+    const size_t nvec = nbytes > head ? (nbytes - head) / 16 : 0;
+    std_mean_kernel<<<stream_grid3(std::max<size_t>(nvec, 1), 256, 6), 256, 0, s>>>(src, nbytes, head, nvec, reinterpret_cast<unsigned long long*>(sums_dev));
     return check_launch("std_mean_kernel");
 }
 

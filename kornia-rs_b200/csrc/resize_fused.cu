@@ -498,19 +498,14 @@ static cudaError_t fr_launch_npx(int npx, bool allfma, unsigned grid, size_t sme
     }
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 int launch_fused_resize_rows(cudaStream_t s, const uint8_t* src, float* dst, const FusedParams& p, uint32_t batch, bool* handled) {
     *handled = false;
     const uint32_t row_bytes = p.sw * 3u;
     // TMA 1-D bulk copies need 16-B aligned rows; very strong downscales have sparse taps (the span would be
     // mostly unused bytes) and stay on the gather kernel.
     if ((row_bytes & 15u) || !aligned16(src) || p.scale_x > 6.0f || p.sw < 16u) return KB200_OK;
-    // developer knobs (tuning sweeps only): KB200_FR_NPX, KB200_FR_STAGES, KB200_FR_CTAS
-    static const int tune_npx = env_int("KB200_FR_NPX", 0), tune_stages = env_int("KB200_FR_STAGES", 0), tune_ctas = env_int("KB200_FR_CTAS", 0);
+    // developer knobs (tuning sweeps only, kb200_debug_set_knob): fr.npx, fr.stages, fr.ctas
+    const int tune_npx = knob(KNOB_FR_NPX), tune_stages = knob(KNOB_FR_STAGES), tune_ctas = knob(KNOB_FR_CTAS);
     // columns per thread: least padding in the last tile (within 2 %); among equals prefer 2, then 3, 1, 4, 5 — the
     // B200 sweep (profiles/r1_cfg2_fused_resize.md) has 2 columns/thread ahead: enough amortisation, many producers.
     int npx = 1;
