@@ -168,82 +168,130 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
-def pick_threads(o, run_once) -> int:
-    """The reference uses rayon on all cores; with OpenMP on a shared / oversubscribed host more threads is not
-    always faster, so time a few candidates briefly and keep the best (reported as `cores`)."""
-    avail = host_threads()
-    cands = sorted({t for t in (avail, 64, 32, 16, 8) if t <= avail}, reverse=True)
-    best, best_t = cands[-1], float("inf")
-    for t in cands:
-        o.set_threads(t)
-        run_once()
-        t0 = time.perf_counter()
-        run_once()
-        dt = time.perf_counter() - t0
-        if dt < best_t:
-            best, best_t = t, dt
-    o.set_threads(best)
-    return best
+_FULL_AFFINITY = None
+
+
+def remember_affinity() -> None:
+    global _FULL_AFFINITY
+    try:
+        _FULL_AFFINITY = os.sched_getaffinity(0)
+    except Exception:
+        _FULL_AFFINITY = None
+
+
+def restore_affinity() -> None:
+    """The GPU arm binds each rank to its GPU's NUMA node; the CPU legs model the reference's rayon pool on ALL host
+    cores, so they run under the affinity the process started with."""
+    if _FULL_AFFINITY:
+        try:
+            os.sched_setaffinity(0, _FULL_AFFINITY)
+        except Exception:
+            pass
+
+
+CPU_ROTATION = 8   # distinct 4K sources in rotation (199 MB): the host L3 cannot hold them (BASELINE.md protocol)
+
+
+class CpuArm:
+    """The reference's CPU implementation of config 2 — the oracle port of resize_normalize_to_tensor_u8_to_f32_bilinear
+    (AVX2+FMA leaf, OpenMP 8-row tasks like rayon) — with ONE procedure shared by `--impl reference` and the
+    `cpu_baseline` leg: 8 rotating sources, thread count chosen once from >= 0.5 s trials per candidate."""
+
+    def __init__(self):
+        from oracle import oracle as o
+
+        self.o = o
+        self.srcs = [o.pattern_u8(SW * SH * 3, 0x12345678 + i).reshape(SH, SW, 3) for i in range(CPU_ROTATION)]
+        self.scale, self.bias = o.normalize_params_from_mean_std(IMAGENET_MEAN, IMAGENET_STD)
+        self.i = 0
+        self.threads = self._pick_threads()
+
+    def frame(self) -> None:
+        self.o.resize_normalize_u8_to_f32_chw(self.srcs[self.i % CPU_ROTATION], DW, DH, self.scale, self.bias, self.o.LEAF_X86)
+        self.i += 1
+
+    def _rate(self, seconds: float) -> float:
+        n, t0 = 0, time.perf_counter()
+        while True:
+            self.frame()
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt >= seconds:
+                return n / dt
+
+    def _pick_threads(self) -> int:
+        avail = host_threads()
+        cands = sorted({t for t in (avail, avail // 2, 64, 32, 16, 8) if 1 <= t <= avail}, reverse=True)
+        best, best_r = cands[-1], 0.0
+        for t in cands:
+            self.o.set_threads(t)
+            self._rate(0.15)            # warm the pool
+            r = self._rate(0.5)
+            if r > best_r:
+                best, best_r = t, r
+        self.o.set_threads(best)
+        return best
+
+    def describe(self, frames: int, seconds: float) -> str:
+        return (f"{frames} frames of config 2 ({CPU_ROTATION} distinct 4K sources in rotation) in {seconds:.1f} s; oracle C++ port of the reference CPU "
+                f"path (AVX2+FMA leaf, OpenMP {self.threads} threads, 8-row tasks like rayon)")
 
 
 def run_reference_arm(args) -> None:
     """The reference's own CPU implementation of the path (oracle port: the Rust crate cannot be built in this
-    image), all host threads, same config/metric.  One step = a bounded sample of the batch."""
+    image), all host threads, same config/metric.  One step = a bounded sample (REF_FRAMES frames) of the batch;
+    the timed region lasts >= 2 s whatever --steps says (steps are repeated until it does)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
-
-    from oracle import oracle as o
-
-    frames = 2  # bounded sample: 2 of the 64 frames per step
-    src = [o.pattern_u8(SW * SH * 3, 0x12345678 + i).reshape(SH, SW, 3) for i in range(frames)]
-    scale, bias = o.normalize_params_from_mean_std(IMAGENET_MEAN, IMAGENET_STD)
-    threads = pick_threads(o, lambda: o.resize_normalize_u8_to_f32_chw(src[0], DW, DH, scale, bias, o.LEAF_X86))
+    arm = CpuArm()
+    frames = 4  # bounded sample: 4 of the 64 frames per step
 
     def step():
-        for f in src:
-            o.resize_normalize_u8_to_f32_chw(f, DW, DH, scale, bias, o.LEAF_X86)
+        for _ in range(frames):
+            arm.frame()
 
     for _ in range(max(1, min(args.warmup, 3))):
         step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    mpix = frames * DW * DH * args.steps / 1e6
-    val = mpix / dt
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        for _ in range(args.steps):
+            step()
+        reps += 1
+        dt = time.perf_counter() - t0
+        if dt >= 2.0:
+            break
+    nsteps = reps * args.steps
+    val = frames * DW * DH * nsteps / 1e6 / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dt / nsteps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{frames} of {BATCH} frames per step"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{frames} frames/step x {args.steps} steps, oracle C++ restatement of "
-                                   "resize_normalize_to_tensor_u8_to_f32_bilinear (AVX2+FMA leaf), OpenMP 8-row tasks"},
+        "config": headline_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": arm.threads, "kind": "port",
+                         "sample": f"{frames} of {BATCH} frames per step; " + arm.describe(frames * nsteps, dt)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
 
 
 def cpu_baseline_sample(budget_s: float = 12.0) -> dict:
-    import numpy as np
-
-    from oracle import oracle as o
-
-    srcs = [o.pattern_u8(SW * SH * 3, 0x12345678 + i).reshape(SH, SW, 3) for i in range(4)]   # 100 MB: rotates past the host L3
-    scale, bias = o.normalize_params_from_mean_std(IMAGENET_MEAN, IMAGENET_STD)
-    threads = pick_threads(o, lambda: o.resize_normalize_u8_to_f32_chw(srcs[0], DW, DH, scale, bias, o.LEAF_X86))
+    arm = CpuArm()
     n, t0 = 0, time.perf_counter()
     while True:
-        o.resize_normalize_u8_to_f32_chw(srcs[n % 4], DW, DH, scale, bias, o.LEAF_X86)
+        arm.frame()
         n += 1
         dt = time.perf_counter() - t0
         if dt > budget_s:
             break
-    return {"value": n * DW * DH / 1e6 / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} frames of config 2 (4 distinct sources in rotation) in {dt:.1f} s (oracle C++ port of the reference CPU path, AVX2+FMA leaf, "
-                      f"OpenMP {threads} threads, 8-row tasks like rayon)"}
+    return {"value": n * DW * DH / 1e6 / dt, "unit": UNIT, "cores": arm.threads, "kind": "port", "sample": arm.describe(n, dt)}
+
+
+def headline_config(n_gpus: int) -> dict:
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": BATCH * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, no data-path collective)",
+            "l2": "inputs larger than L2: each step walks a 1.59 GB source batch (0.53 GB of tapped rows read) + 0.71 GB destination",
+            "leaf": "x86 AVX2+FMA leaf of the reference (bit-identical)"}
 
 
 def time_launches(fn, iters: int, warmup: int, stream) -> float:
@@ -262,102 +310,193 @@ def time_launches(fn, iters: int, warmup: int, stream) -> float:
     return e0.elapsed_time(e1) / iters
 
 
-def op_table(kb, dev, peak_gbs: float, quick: bool) -> dict:
-    """Per-op kernel timings for the other hot-path rows (inputs > L2 or rotated; CUDA events)."""
+H_CFG5 = [1.02, 0.03, -40.0, -0.03, 1.01, 25.0, 2.0e-6, 1.2e-6, 1.0]   # SURVEY §8(d) cfg 5
+
+
+def load_ref_gpu(dev):
+    """The GPU baseline (the reference's own kernels, baseline/ref_gpu.py) — None when baseline/_ref was not built."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import ref_gpu
+
+        if not ref_gpu.available():
+            return None
+        return ref_gpu.RefGpu(dev.index or 0)
+    except Exception as ex:  # the table must survive a missing driver binding
+        log(f"[bench] reference GPU kernels unavailable: {ex!r}")
+        return None
+
+
+def op_table(kb, dev, peak_gbs: float, quick: bool, n_gpus: int, rank: int) -> dict:
+    """Every hot-path op at N GPUs: each rank runs the op on ITS shard (weak scaling: cfg 3 = 256 frames per GPU,
+    cfg 4 = 16 images per GPU, cfg 5 = 64 images per GPU — at N = 8 exactly BASELINE's 128 / 512-image configs), inputs
+    from SURVEY §8(d)'s generators, CUDA events on the launch stream, MAX over ranks; Mpix/s is the whole job's.
+    `ref_gpu_ms` / `vs_ref_gpu`: the reference's own CUDA kernels (NVRTC compute_100, fmad=false, 32x8 / 256-thread
+    launches, one launch per image) timed on rank 0 on the SAME buffers."""
+    import numpy as np
     import torch
+
+    import ctypes as C
+
+    def preprocess_affine(mode, sw, sh, dw, dh):        # Affine::new through the product's host helper
+        a = (C.c_float * 4)()
+        kb._lib.lib().kb200_preprocess_affine(0 if mode == kb.ResizeMode.Letterbox else 1, sw, sh, dw, dh, a)
+        return tuple(a)
+
+    def tapped_pixels(sw, sh, dw, dh, fused):
+        """Distinct source pixels addressed by >= 1 tap (SURVEY §8(d)'s algorithmic-bytes rule), from the samplers' own
+        f32 coordinate expressions (resize/mod.rs:161-179; resize/fused.rs:196-201); separable, so nx * ny."""
+        def axis(s_len, d_len):
+            i = np.arange(d_len, dtype=np.float32)
+            a = np.float32(s_len) / np.float32(d_len)
+            if fused:
+                f = np.maximum((i + np.float32(0.5)) * a - np.float32(0.5), np.float32(0))
+            else:
+                f = np.minimum(np.maximum(a * i + (np.float32(0.5) * a - np.float32(0.5)), np.float32(0)), np.float32(s_len - 1))
+            i0 = np.minimum(f.astype(np.int64), s_len - 1)
+            i1 = np.minimum(i0 + 1, s_len - 1)
+            return len(np.union1d(i0, i1))
+        return axis(sw, dw) * axis(sh, dh)
 
     st = torch.cuda.current_stream(dev)
     out = {}
-
-    def rec(name, ms, units_mpix, alg_bytes, note=""):
-        gbs = alg_bytes / (ms * 1e-3) / 1e9
-        out[name] = {"ms": round(ms, 4), "mpix_s": round(units_mpix / (ms * 1e-3), 1), "alg_gb": round(alg_bytes / 1e9, 4),
-                     "gbs": round(gbs, 1), "frac": round(gbs / peak_gbs, 3), **({"note": note} if note else {})}
-
+    ref = load_ref_gpu(dev) if rank == 0 else None
     it, wu = (5, 3) if quick else (20, 5)
-    g = torch.Generator(device=dev).manual_seed(1234)
-    # config 3a / 3b: NV12 1080p x 256 -> CHW
+    rit, rwu = (2, 1) if quick else (4, 2)
+
+    def rec(name, fn, units_mpix, alg_bytes, batch, note="", ref_fn=None):
+        kb.dist.barrier(dev)
+        ms = kb.dist.max_over_ranks(time_launches(fn, it, wu, st), dev)
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        row = {"ms": round(ms, 4), "mpix_s": round(n_gpus * units_mpix / (ms * 1e-3), 1), "alg_gb_per_gpu": round(alg_bytes / 1e9, 4),
+               "gbs_per_gpu": round(gbs, 1), "frac": round(gbs / peak_gbs, 3), "batch_per_gpu": batch, "kernel": kb._lib.last_kernel()}
+        if note:
+            row["note"] = note
+        if ref is not None and ref_fn is not None:
+            try:
+                rms = time_launches(ref_fn, rit, rwu, st)
+                row["ref_gpu_ms"] = round(rms, 4)
+                row["vs_ref_gpu"] = round(rms / time_launches(fn, rit, rwu, st), 2)   # same-rank, same-moment ratio
+            except Exception as ex:
+                row["ref_gpu_error"] = repr(ex)
+        kb.dist.barrier(dev)
+        out[name] = row
+
+    first = rank   # this rank's units start at global index rank * share
+
+    # ── config 3: NV12 1080p frames, bytes ((i*7+13) % 251) + 31k (preprocess.rs:1765-1767) ────────────────────────
     w, h, n = 1920, 1080, 64 if quick else 256
     frame = w * h * 3 // 2
-    raw = torch.randint(0, 256, (n, frame), dtype=torch.uint8, device=dev, generator=g)
+    base = ((torch.arange(frame, device=dev, dtype=torch.int64) * 7 + 13) % 251)
+    raw = torch.empty((n, frame), dtype=torch.uint8, device=dev)
+    for k in range(n):
+        raw[k] = ((base + 31 * (first * n + k)) & 0xFF).to(torch.uint8)
+    del base
     frames = [raw[i] for i in range(n)]
-    pre = kb.Preprocessor.builder().source_format(kb.SourceFormat.Nv12).mode(kb.ResizeMode.Stretch).normalize(kb.Normalize.imagenet()).build_cuda()
-    dst = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
-    ms = time_launches(lambda: pre.run_raw_batch(frames, w, h, dst), it, wu, st)
-    rec("cfg3a_nv12_1080p_to_chw1080p", ms, n * w * h / 1e6, n * (frame + 3 * w * h * 4), f"batch {n}, one launch")
-    del dst
-    pre = kb.Preprocessor.builder().source_format(kb.SourceFormat.Nv12).mode(kb.ResizeMode.Letterbox).normalize(kb.Normalize.imagenet()).build_cuda()
-    dst = torch.empty((n, 3, 640, 640), dtype=torch.float32, device=dev)
-    ms = time_launches(lambda: pre.run_raw_batch(frames, w, h, dst), it, wu, st)
-    # distinct source bytes the reference algorithm addresses, counted exactly by the oracle
-    # (tests/test_abi_and_host.py::test_cfg3b_algorithmic_bytes): 1,958,400 B/frame (+ 4,915,200 B destination).
-    # The CUDA kernel skips the zero-weight +1 taps of this exact 3:1 decimation, so it moves fewer source bytes than that.
-    rec("cfg3b_nv12_1080p_letterbox640", ms, n * 640 * 640 / 1e6, n * (1958400 + 3 * 640 * 640 * 4), f"batch {n}; oracle-counted tap bytes")
+    inv_std = [float(np.float32(1.0) / np.float32(v)) for v in IMAGENET_STD]
+    for tag, mode, (dw, dh), src_bytes in (("cfg3a_nv12_1080p_to_chw1080p", kb.ResizeMode.Stretch, (w, h), frame),
+                                           ("cfg3b_nv12_1080p_letterbox640", kb.ResizeMode.Letterbox, (640, 640), 1958400)):
+        pre = kb.Preprocessor.builder().source_format(kb.SourceFormat.Nv12).mode(mode).normalize(kb.Normalize.imagenet()).build_cuda()
+        dst = torch.empty((n, 3, dh, dw), dtype=torch.float32, device=dev)
+        aff = preprocess_affine(mode, w, h, dw, dh)
+        rec(tag, lambda: pre.run_raw_batch(frames, w, h, dst), n * dw * dh / 1e6, n * (src_bytes + 3 * dw * dh * 4), n,
+            "one launch per batch; 3b source bytes = distinct tapped bytes, counted by tests/test_abi_and_host.py::test_cfg3b_algorithmic_bytes",
+            ref_fn=(lambda: ref.preprocess(frames, w, h, dst, aff, IMAGENET_MEAN, inv_std, 114.0)) if ref else None)
+        del dst
     rgb = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.uint8, dev, batch=n)
-    ms = time_launches(lambda: kb.imgproc.rgb_from_nv12(raw, rgb), it, wu, st)
-    rec("rgb_from_nv12_1080p", ms, n * w * h / 1e6, n * (frame + w * h * 3), f"batch {n}")
-    del raw, frames, dst, rgb
-    # config 4: gaussian 5x5 σ1.5 then sobel 3 on 4K f32 x 16 (per-GPU share)
-    w, h, n = 3840, 2160, 4 if quick else 16
-    src = kb.Image(torch.rand((n, h, w, 3), dtype=torch.float32, device=dev, generator=g))
-    a = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=n)
-    b = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=n)
-    ms = time_launches(lambda: kb.imgproc.gaussian_blur(src, a, (5, 5), (1.5, 1.5)), it, wu, st)
-    rec("cfg4_gaussian5x5_4k_f32", ms, n * w * h / 1e6, n * w * h * 3 * 4 * 2, f"batch {n}")
-    ms = time_launches(lambda: kb.imgproc.sobel(a, b, 3), it, wu, st)
-    rec("cfg4_sobel3_4k_f32", ms, n * w * h / 1e6, n * w * h * 3 * 4 * 2, f"batch {n}")
-    # config 5: warp_perspective 4K f32
-    H = [1.02, 0.03, -40.0, -0.03, 1.01, 25.0, 2.0e-6, 1.2e-6, 1.0]
-    ms = time_launches(lambda: kb.imgproc.warp_perspective(src, b, H, kb.InterpolationMode.Bilinear), it, wu, st)
-    rec("cfg5_warp_perspective_4k_f32", ms, n * w * h / 1e6, n * w * h * 3 * 4 * 2, f"batch {n}; alg bytes ≈ full src + dst")
+    rec("rgb_from_nv12_1080p", lambda: kb.imgproc.rgb_from_nv12(raw, rgb), n * w * h / 1e6, n * (frame + w * h * 3), n,
+        ref_fn=(lambda: ref.rgb_from_nv12(raw, rgb.data, w, h)) if ref else None)
+    del raw, frames, rgb
+
+    # ── 4K f32 sources: pattern_f32 = pattern_u8 / 255, seed 0x12345678 + image index (cuda/color/mod.rs:303-321) ──
+    w, h = 3840, 2160
+    n5 = 8 if quick else 64          # config 5 share
+    n4 = 4 if quick else 16          # config 4 share
+    gen = LcgPattern(w * h * 3, dev)
+    src5 = torch.empty((n5, h, w, 3), dtype=torch.float32, device=dev)
+    tmp = torch.empty(w * h * 3, dtype=torch.uint8, device=dev)
+    for i in range(n5):
+        gen.frame(0x12345678 + first * n5 + i, tmp)
+        src5[i] = (tmp.to(torch.float32) / 255.0).view(h, w, 3)
+    u8src = torch.empty((n4, h, w, 3), dtype=torch.uint8, device=dev)
+    for i in range(n4):
+        gen.frame(0x0BADF00D + first * n4 + i, u8src[i].view(-1))
+    del gen, tmp
+    S5 = kb.Image(src5)
+    S4 = kb.Image(src5[:n4])
+    px = w * h
+    full = px * 3 * 4 * 2          # src + dst bytes of one 4K f32 image
+
+    # config 5: warp_perspective
+    d5 = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=n5)
+    hinv = kb.imgproc.invert_homography(H_CFG5)
+    rec("cfg5_warp_perspective_4k_f32", lambda: kb.imgproc.warp_perspective(S5, d5, H_CFG5, kb.InterpolationMode.Bilinear), n5 * px / 1e6, n5 * full, n5,
+        "alg bytes = full src + dst (>= 97 % of the source is addressed)",
+        ref_fn=(lambda: ref.warp("perspective", "bilinear", src5, d5.data, hinv)) if ref else None)
+    del d5
+    a = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=n4)
+    b = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=n4)
     M = kb.imgproc.get_rotation_matrix2d((w / 2, h / 2), 30.0, 1.0)
-    ms = time_launches(lambda: kb.imgproc.warp_affine(src, b, M, kb.InterpolationMode.Bilinear), it, wu, st)
-    rec("warp_affine_rot30_4k_f32", ms, n * w * h / 1e6, n * w * h * 3 * 4 * 2, f"batch {n}")
-    # a1: f32 HWC resize 4K -> 720p
-    small = kb.Image.zeros_cuda(kb.ImageSize(1280, 720), 3, torch.float32, dev, batch=n)
-    ms = time_launches(lambda: kb.imgproc.resize(src, small, kb.InterpolationMode.Bilinear), it, wu, st)
-    rec("resize_f32_4k_to_720p", ms, n * 1280 * 720 / 1e6, n * (44236800 + 11059200), f"batch {n}")
-    # extras: gray f32, normalize, std_mean
-    gray = kb.Image.zeros_cuda(kb.ImageSize(w, h), 1, torch.float32, dev, batch=n)
-    ms = time_launches(lambda: kb.imgproc.gray_from_rgb(src, gray), it, wu, st)
-    rec("gray_from_rgb_f32_4k", ms, n * w * h / 1e6, n * w * h * 16, f"batch {n}")
-    ms = time_launches(lambda: kb.imgproc.normalize_mean_std(src, a, IMAGENET_MEAN, IMAGENET_STD), it, wu, st)
-    rec("normalize_mean_std_4k_f32", ms, n * w * h / 1e6, n * w * h * 24, f"batch {n}")
-    del src, a, b, small, gray
-    u8 = kb.Image(torch.randint(0, 256, (n * 4, h, w, 3), dtype=torch.uint8, device=dev, generator=g))
-    ms = time_launches(lambda: kb.imgproc.std_mean_sums(u8), it, wu, st)
-    rec("std_mean_4k_u8", ms, n * 4 * w * h / 1e6, n * 4 * w * h * 3, f"batch {4 * n}")
-    # SURVEY §8(f) "next" rows (u8 twins, remap): functional + bit-exact this round, not yet tuned
-    nb = n                                   # reuse the first `n` u8 frames
-    s8 = kb.Image(u8.data[:nb])
-    d8 = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.uint8, dev, batch=nb)
-    half = kb.Image.zeros_cuda(kb.ImageSize(w // 2, h // 2), 3, torch.uint8, dev, batch=nb)
-    px = nb * w * h
-    ms = time_launches(lambda: kb.imgproc.resize_fast_u8(s8, half, kb.InterpolationMode.Bilinear), it, wu, st)
-    rec("next_resize_fast_u8_pyrdown_4k_to_1080p", ms, px / 4 / 1e6, px * 3 + px * 3 // 4, f"batch {nb}")
-    third = kb.Image.zeros_cuda(kb.ImageSize(w // 3, h // 3), 3, torch.uint8, dev, batch=nb)
-    ms = time_launches(lambda: kb.imgproc.resize_fast_u8(s8, third, kb.InterpolationMode.Bilinear), it, wu, st)
-    rec("next_resize_fast_u8_4k_to_720p", ms, px / 9 / 1e6, px * 3 * 4 // 9 + px * 3 // 9, f"batch {nb}; u8 twin of config 2 (4/9 of the source + destination)")
-    del third
-    ms = time_launches(lambda: kb.imgproc.warp_perspective_u8(s8, d8, H), it, wu, st)
-    rec("next_warp_perspective_u8_4k", ms, px / 1e6, px * 3 * 2, f"batch {nb}")
-    ms = time_launches(lambda: kb.imgproc.warp_affine_u8(s8, d8, M), it, wu, st)
-    rec("next_warp_affine_u8_rot30_4k", ms, px / 1e6, px * 3 * 2, f"batch {nb}")
-    ms = time_launches(lambda: kb.imgproc.gaussian_blur_u8(s8, d8, (5, 5), (1.5, 1.5)), it, wu, st)
-    rec("next_gaussian_blur_u8_5x5_4k", ms, px / 1e6, px * 3 * 2, f"batch {nb}")
+    minv = kb.imgproc.invert_affine_transform(M)
+    rec("warp_affine_rot30_4k_f32", lambda: kb.imgproc.warp_affine(S4, b, M, kb.InterpolationMode.Bilinear), n4 * px / 1e6, n4 * full, n4,
+        ref_fn=(lambda: ref.warp("affine", "bilinear", src5[:n4], b.data, minv)) if ref else None)
+    # config 4: gaussian 5x5 sigma 1.5, then sobel 3 on its output
+    scratch = torch.empty((h, w, 3), dtype=torch.float32, device=dev) if ref else None
+    taps = kb.imgproc.gaussian_kernel_1d(5, 1.5) if ref else None
+    rec("cfg4_gaussian5x5_4k_f32", lambda: kb.imgproc.gaussian_blur(S4, a, (5, 5), (1.5, 1.5)), n4 * px / 1e6, n4 * full, n4,
+        ref_fn=(lambda: ref.separable_filter(src5[:n4], b.data, scratch, taps, taps)) if ref else None)
+    gx = torch.empty((1, h, w, 3), dtype=torch.float32, device=dev) if ref else None
+    gy = torch.empty((1, h, w, 3), dtype=torch.float32, device=dev) if ref else None
+    rec("cfg4_sobel3_4k_f32", lambda: kb.imgproc.sobel(a, b, 3), n4 * px / 1e6, n4 * full, n4,
+        ref_fn=(lambda: ref.sobel(a.data, b.data, scratch, gx, gy, 3)) if ref else None)
+    del scratch, gx, gy
+    # a1: f32 HWC bilinear resize at three ratios (3:1 exact, 2:1 exact = the reference's published config, 2.4:1)
+    for dw, dh in ((1280, 720), (1920, 1080), (1600, 900)):
+        small = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev, batch=n4)
+        tapped = tapped_pixels(w, h, dw, dh, False)
+        rec(f"resize_f32_4k_to_{dw}x{dh}", lambda: kb.imgproc.resize(S4, small, kb.InterpolationMode.Bilinear), n4 * dw * dh / 1e6,
+            n4 * (tapped * 12 + dw * dh * 12), n4, f"distinct tapped source pixels: {tapped}",
+            ref_fn=(lambda: ref.resize_bilinear(src5[:n4], small.data)) if ref else None)
+        del small
+    gray = kb.Image.zeros_cuda(kb.ImageSize(w, h), 1, torch.float32, dev, batch=n4)
+    rec("gray_from_rgb_f32_4k", lambda: kb.imgproc.gray_from_rgb(S4, gray), n4 * px / 1e6, n4 * px * 16, n4,
+        ref_fn=(lambda: ref.gray_f32(src5[:n4], gray.data)) if ref else None)
+    rec("normalize_mean_std_4k_f32", lambda: kb.imgproc.normalize_mean_std(S4, a, IMAGENET_MEAN, IMAGENET_STD), n4 * px / 1e6, n4 * px * 24, n4)
+    del gray
+
+    # a2 beyond the headline geometry: every mode of the fused u8 -> f32 CHW resize (the headline runs FR_POINT)
+    sc, bi = kb.imgproc.NormalizeParams.from_mean_std(IMAGENET_MEAN, IMAGENET_STD).scale, kb.imgproc.NormalizeParams.from_mean_std(IMAGENET_MEAN, IMAGENET_STD).bias
+    for tag, sw_, (dw, dh) in (("fused_resize_u8_4k_to_1080p_box2x", w, (1920, 1080)), ("fused_resize_u8_4k_to_1600x900_general", w, (1600, 900)),
+                               ("fused_resize_u8_3838w_to_720p_gather_fallback", 3838, (1280, 720))):
+        s8 = u8src if sw_ == w else u8src.view(n4, -1)[:, :h * sw_ * 3].reshape(n4, h, sw_, 3)
+        dstc = torch.empty((n4, 3, dh, dw), dtype=torch.float32, device=dev)
+        tapped = tapped_pixels(sw_, h, dw, dh, True)
+        rec(tag, lambda: kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(s8, dw, dh, sc, bi, out=dstc), n4 * dw * dh / 1e6,
+            n4 * (tapped * 3 + dw * dh * 12), n4, f"distinct tapped source pixels: {tapped}")
+        del dstc
+    rec("std_mean_4k_u8", lambda: kb.imgproc.std_mean_sums(kb.Image(u8src)), n4 * px / 1e6, n4 * px * 3, n4)
+
+    # ── SURVEY §8(f) rows: u8 twins, remap ───────────────────────────────────────────────────────────────────────
+    s8 = kb.Image(u8src)
+    d8 = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.uint8, dev, batch=n4)
+    tot = n4 * px
+    half = kb.Image.zeros_cuda(kb.ImageSize(w // 2, h // 2), 3, torch.uint8, dev, batch=n4)
+    rec("next_resize_fast_u8_pyrdown_4k_to_1080p", lambda: kb.imgproc.resize_fast_u8(s8, half, kb.InterpolationMode.Bilinear), tot / 4 / 1e6, tot * 3 + tot * 3 // 4, n4)
+    third = kb.Image.zeros_cuda(kb.ImageSize(w // 3, h // 3), 3, torch.uint8, dev, batch=n4)
+    rec("next_resize_fast_u8_4k_to_720p", lambda: kb.imgproc.resize_fast_u8(s8, third, kb.InterpolationMode.Bilinear), tot / 9 / 1e6, tot * 3 * 4 // 9 + tot * 3 // 9, n4,
+        "u8 twin of config 2 (4/9 of the source + destination)")
+    del third, half
+    rec("next_warp_perspective_u8_4k", lambda: kb.imgproc.warp_perspective_u8(s8, d8, H_CFG5), tot / 1e6, tot * 6, n4)
+    rec("next_warp_affine_u8_rot30_4k", lambda: kb.imgproc.warp_affine_u8(s8, d8, M), tot / 1e6, tot * 6, n4)
+    rec("next_gaussian_blur_u8_5x5_4k", lambda: kb.imgproc.gaussian_blur_u8(s8, d8, (5, 5), (1.5, 1.5)), tot / 1e6, tot * 6, n4)
     yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
     r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / float(w * w)
     mx = kb.Image((w / 2 + (xx - w / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())
     my = kb.Image((h / 2 + (yy - h / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())
     del yy, xx, r2
-    ms = time_launches(lambda: kb.imgproc.remap_u8(s8, d8, mx, my, kb.InterpolationMode.Bilinear), it, wu, st)
-    rec("next_remap_u8_4k", ms, px / 1e6, px * 3 * 2 + w * h * 8, f"batch {nb}; radial-distortion map shared by the batch")
-    del u8, s8, d8, half
-    nf = max(2, nb // 2)
-    sf = kb.Image(torch.rand((nf, h, w, 3), dtype=torch.float32, device=dev, generator=g))
-    df = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=nf)
-    ms = time_launches(lambda: kb.imgproc.remap(sf, df, mx, my, kb.InterpolationMode.Bilinear), it, wu, st)
-    rec("next_remap_f32_4k", ms, nf * w * h / 1e6, nf * w * h * 24 + w * h * 8, f"batch {nf}")
+    rec("next_remap_u8_4k", lambda: kb.imgproc.remap_u8(s8, d8, mx, my, kb.InterpolationMode.Bilinear), tot / 1e6, tot * 6 + px * 8, n4, "radial-distortion map shared by the batch")
+    rec("next_remap_f32_4k", lambda: kb.imgproc.remap(S4, a, mx, my, kb.InterpolationMode.Bilinear), tot / 1e6, tot * 24 + px * 8, n4,
+        ref_fn=(lambda: ref.remap(src5[:n4], a.data, mx.data, my.data)) if ref else None)
     return out
 
 
@@ -384,7 +523,8 @@ def main() -> None:
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback on the product path)")
-    dev = kb.dist.init_from_env()
+    remember_affinity()
+    dev = kb.dist.init_from_env()      # binds this rank to its GPU's NUMA node before any pinned allocation
     rank, ws = kb.dist.rank(), kb.dist.world_size()
     if ws != args.gpus and ws > 1:
         log(f"[bench] WORLD_SIZE={ws} differs from --gpus={args.gpus}; using WORLD_SIZE")
@@ -429,11 +569,19 @@ def main() -> None:
     alg_bytes = BATCH * (SW * SH * 3 * 4 // 9 + DW * DH * 3 * 4)  # 22,118,400 B/frame (SURVEY §8(d) cfg 2)
     ms_launch = e0.elapsed_time(e1) / args.steps
     achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
-    traffic = None
+    # dram bytes of this kernel from the committed ncu --set full capture — only if the capture was taken from the
+    # kernel source that is running now (hash recorded with it); a stale capture reports null, never a stale number
+    traffic, traffic_src = None, "no ncu capture recorded for the current kernel source"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("fused_resize_cfg2_bytes_per_launch")
+            import hashlib
+
+            tj = json.load(open(tpath))
+            cur = hashlib.sha256(open(os.path.join(ROOT, "kornia-rs_b200", "csrc", "resize_fused.cu"), "rb").read()).hexdigest()[:16]
+            if tj.get("fused_resize_cfg2_source_sha16") == cur:
+                traffic = tj.get("fused_resize_cfg2_bytes_per_launch")
+                traffic_src = tj.get("fused_resize_cfg2_capture", "profiles/traffic.json")
         except Exception:
             traffic = None
 
@@ -474,6 +622,8 @@ def main() -> None:
         del host_src, host_dst
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
                "ms_per_step": e2e_ms, "steps": e2e_steps, "matches_device_result": same,
+               "h2d_gbs_per_rank": round(h2d_step / (e2e_ms * 1e-3) / 1e9, 1), "d2h_gbs_per_rank": round(d2h_step / (e2e_ms * 1e-3) / 1e9, 1),
+               "numa": kb.dist.numa_binding(),
                "host_src_bytes_per_step": BATCH * SW * SH * 3, "row_map": list(row_map),
                "how": f"kb200_resize_normalize_chw_u8_f32_host on pinned host buffers: chunks of <= {chunk} frames over a {nstreams}-stream ring "
                       f"(strided upload of the tapped source rows only — period/first/keep = {row_map} — kernel, download)"}
@@ -481,13 +631,17 @@ def main() -> None:
     del src, dst
 
     ops = None
-    if rank == 0 and not args.no_ops and n_gpus == 1:
+    if not args.no_ops:   # every rank takes part (each op is timed on every shard, max over ranks)
         try:
-            ops = op_table(kb, dev, peak_gbs, args.quick)
+            ops = op_table(kb, dev, peak_gbs, args.quick, n_gpus, rank)
         except Exception as ex:  # the headline must survive an op failing
+            import traceback
+
+            log(traceback.format_exc())
             ops = {"error": repr(ex)}
     cpu = None
     if rank == 0 and not args.no_cpu and n_gpus == 1:
+        restore_affinity()
         try:
             cpu = cpu_baseline_sample(4.0 if args.quick else 12.0)
         except Exception as ex:
@@ -497,13 +651,12 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": BATCH * n_gpus, "parallelism": f"dp{n_gpus} (batch shards, no data-path collective)",
-                       "l2": "inputs larger than L2: each step walks a 1.59 GB source batch (0.53 GB of tapped rows read) + 0.71 GB destination",
-                       "leaf": "x86 AVX2+FMA leaf of the reference (bit-identical)"},
+            "config": headline_config(n_gpus),
             "e2e": e2e,
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "traffic": traffic, "frac_of_traffic": (traffic / (ms_launch * 1e-3) / 1e9 / peak_gbs) if traffic else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "frac_of_traffic": (traffic / (ms_launch * 1e-3) / 1e9 / peak_gbs) if traffic else None,
                          "note": "algorithmic bytes count all four taps per pixel (SURVEY 8(d)); at 3:1 three have weight exactly 0 and are "
                                  "not fetched, so the bytes moved (traffic) are below the algorithmic bytes and frac can exceed 1; "
                                  "frac_of_traffic = bytes actually moved / time / peak",

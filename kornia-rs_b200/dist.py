@@ -54,14 +54,82 @@ def world_size() -> int:
     return td.get_world_size() if is_initialized() else 1
 
 
-def init_from_env(backend: str | None = None) -> torch.device:
+_numa_state: dict = {}
+
+
+def gpu_cpu_affinity(index: int) -> list[int]:
+    """CPUs local to GPU `index` (NVML's ideal affinity = the cores of the NUMA node its PCIe root hangs off)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        return [c for c in cpus if c < ncpu]
+    except Exception:
+        return []
+
+
+def _node_of_cpu(cpu: int) -> int | None:
+    try:
+        for name in os.listdir(f"/sys/devices/system/cpu/cpu{cpu}"):
+            if name.startswith("node") and name[4:].isdigit():
+                return int(name[4:])
+    except OSError:
+        pass
+    return None
+
+
+def bind_to_gpu_numa(index: int) -> dict:
+    """Pin this process (threads created later inherit it) to the CPUs of the GPU's NUMA node and prefer that node for
+    memory, BEFORE any pinned host buffer is allocated: page-locked staging memory is then first-touched on the socket
+    the GPU's PCIe root belongs to, so host<->device copies never cross the inter-socket link.  Round-1 measurement:
+    without this, 4 ranks sharing a socket ran their e2e step at 27 ms instead of 15 ms (SCALE_r01).
+    Returns what was done (reported by bench.py); every step is best effort."""
+    info = {"gpu": index, "cpus": None, "node": None, "mempolicy": None}
+    cpus = gpu_cpu_affinity(index)
+    try:
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = f"{len(cpus)} cpus ({min(cpus)}..{max(cpus)})"
+    except (AttributeError, OSError) as e:
+        info["cpus"] = f"unchanged ({e})"
+    node = _node_of_cpu(cpus[0]) if cpus else None
+    info["node"] = node
+    if node is not None:
+        try:  # set_mempolicy(MPOL_PREFERRED = 1, nodemask, maxnode) — x86_64 syscall 238
+            import ctypes
+
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            rc = libc.syscall(238, 1, mask, 16 * 64 + 1)
+            info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+        except Exception as e:  # no libc syscall wrapper: first-touch under the affinity above still places pages locally
+            info["mempolicy"] = f"skipped ({e})"
+    _numa_state.update(info)
+    return info
+
+
+def numa_binding() -> dict:
+    return dict(_numa_state)
+
+
+def init_from_env(backend: str | None = None, bind_numa: bool = True) -> torch.device:
     """Join the job described by RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT (torchrun).
-    Returns this rank's device.  A single-process run (no WORLD_SIZE) does not create a process group."""
+    Returns this rank's device.  A single-process run (no WORLD_SIZE) does not create a process group.
+    With `bind_numa` the process is first bound to its GPU's NUMA node (see bind_to_gpu_numa)."""
     ws = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cuda = torch.cuda.is_available()
     dev = torch.device(f"cuda:{local}") if cuda else torch.device("cpu")
     if cuda:
+        if bind_numa:
+            bind_to_gpu_numa(local)
         torch.cuda.set_device(dev)
     if ws > 1 and not is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
