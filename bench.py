@@ -366,7 +366,16 @@ def op_table(kb, dev, peak_gbs: float, quick: bool, n_gpus: int, rank: int) -> d
 
     def rec(name, fn, units_mpix, alg_bytes, batch, note="", ref_fn=None):
         kb.dist.barrier(dev)
-        ms = kb.dist.max_over_ranks(time_launches(fn, it, wu, st), dev)
+        try:
+            ms_local = time_launches(fn, it, wu, st)
+        except Exception as ex:   # one failing row must not take the table down (all ranks still meet at the collectives)
+            log(f"[bench] op {name} failed: {ex!r}")
+            ms_local = float("nan")
+        ms = kb.dist.max_over_ranks(ms_local if ms_local == ms_local else 1e30, dev)
+        if not (ms < 1e29):
+            out[name] = {"error": "failed on at least one rank (see stderr)"}
+            kb.dist.barrier(dev)
+            return
         gbs = alg_bytes / (ms * 1e-3) / 1e9
         row = {"ms": round(ms, 4), "mpix_s": round(n_gpus * units_mpix / (ms * 1e-3), 1), "alg_gb_per_gpu": round(alg_bytes / 1e9, 4),
                "gbs_per_gpu": round(gbs, 1), "frac": round(gbs / peak_gbs, 3), "batch_per_gpu": batch, "kernel": kb._lib.last_kernel()}
@@ -468,7 +477,7 @@ def op_table(kb, dev, peak_gbs: float, quick: bool, n_gpus: int, rank: int) -> d
     sc, bi = kb.imgproc.NormalizeParams.from_mean_std(IMAGENET_MEAN, IMAGENET_STD).scale, kb.imgproc.NormalizeParams.from_mean_std(IMAGENET_MEAN, IMAGENET_STD).bias
     for tag, sw_, (dw, dh) in (("fused_resize_u8_4k_to_1080p_box2x", w, (1920, 1080)), ("fused_resize_u8_4k_to_1600x900_general", w, (1600, 900)),
                                ("fused_resize_u8_3838w_to_720p_gather_fallback", 3838, (1280, 720))):
-        s8 = u8src if sw_ == w else u8src.view(n4, -1)[:, :h * sw_ * 3].reshape(n4, h, sw_, 3)
+        s8 = u8src if sw_ == w else u8src.view(n4, -1)[:, :h * sw_ * 3].contiguous().view(n4, h, sw_, 3)
         dstc = torch.empty((n4, 3, dh, dw), dtype=torch.float32, device=dev)
         tapped = tapped_pixels(sw_, h, dw, dh, True)
         rec(tag, lambda: kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(s8, dw, dh, sc, bi, out=dstc), n4 * dw * dh / 1e6,

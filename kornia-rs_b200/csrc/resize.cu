@@ -279,6 +279,9 @@ __global__ void __launch_bounds__(256) resize_nearest_u8_kernel(const uint8_t* _
     }
 }
 
+int launch_resize_rows_f32(int mode, cudaStream_t s, const float* src, float* dst, uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh,
+                           uint32_t batch, float ax, float bx, float ay, float by, const float* mean, const float* inv_std, bool* handled);   // resize_rows.cu
+
 static inline int check_batch(uint32_t batch) {
     if (batch > 65535u) return fail(KB200_ERR_INVALID_ARGUMENT, "batch %u exceeds 65535 per call", batch);
     return KB200_OK;
@@ -305,6 +308,11 @@ static int launch_resize_c3(int mode, kb200_stream_t stream, const float* src, s
     mapping_coeffs(mapping, sh, dh, &m.ay, &m.by);
     dim3 block(32, 8), grid(div_up(dw, 32), div_up(dh, 8), batch);
     cudaStream_t s = as_stream(stream);
+    if (mode != 0) {   // bilinear: the row-streaming kernel (resize_rows.cu) whenever the geometry allows TMA row copies
+        bool handled = false;
+        KB200_TRY(launch_resize_rows_f32(mode, s, src, dst, sw, sh, dw, dh, batch, m.ax, m.bx, m.ay, m.by, mn, is, &handled));
+        if (handled) return KB200_OK;
+    }
     if (mode == 0) resize_f32_c3_kernel<0><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, m, 0, 0, 0, 1, 1, 1);
     else if (mode == 1) resize_f32_c3_kernel<1><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, m, 0, 0, 0, 1, 1, 1);
     else resize_f32_c3_kernel<2><<<grid, block, 0, s>>>(src, dst, sw, sh, dw, dh, m, mn[0], mn[1], mn[2], is[0], is[1], is[2]);

@@ -253,3 +253,73 @@ def test_find_min_max_nan_first(kb, dev):
     assert np.isnan(mn) and np.isnan(mx)
     b = torch.tensor([1.0, float("nan"), -2.0, 5.0], device=dev).reshape(1, 4, 1)
     assert kb.imgproc.find_min_max(kb.Image(b)) == (-2.0, 5.0)
+
+
+# ── a1: f32 HWC resize — the row-streaming kernel and its fallback, named ───────
+@pytest.mark.parametrize("sw,sh,dw,dh,kernel", [
+    (384, 216, 128, 72, "resize_rows_f32_kernel"),     # 3:1 exact (weights 0, all four taps still fetched)
+    (640, 360, 320, 180, "resize_rows_f32_kernel"),    # 2:1
+    (640, 360, 212, 120, "resize_rows_f32_kernel"),    # non-integer ratio
+    (64, 48, 128, 96, "resize_rows_f32_kernel"),       # 2x upscale (y1 == y0 rows, x1 == x0 at the right edge)
+    (1280, 16, 1000, 37, "resize_rows_f32_kernel"),    # several column tiles, ragged last tile, vertical upscale
+    (129, 97, 64, 48, "resize_f32_c3_kernel"),         # sw % 4 != 0 -> gather fallback
+    (128, 96, 66, 50, "resize_f32_c3_kernel"),         # dw % 4 != 0 -> gather fallback
+])
+def test_resize_f32_rows_named(kb, oracle, dev, sw, sh, dw, dh, kernel):
+    n = 3
+    src = oracle.pattern_f32(n * sw * sh * 3).reshape(n, sh, sw, 3)
+    dst = kb.Image.from_size_val(kb.ImageSize(dw, dh), -1.0, 3, torch.float32, dev, batch=n)
+    kb.imgproc.resize(kb.Image(cu(src, dev)), dst, kb.InterpolationMode.Bilinear)
+    assert last_kernel(kb) == kernel, last_kernel(kb)
+    want = np.stack([oracle.resize_f32(src[i], dw, dh) for i in range(n)])
+    assert_f32_equal(dst.numpy(), want, f"resize rows {sw}x{sh}->{dw}x{dh}")
+
+
+def test_resize_f32_rows_nonfinite_taps(kb, oracle, dev):
+    """A zero-weight tap on inf must give NaN exactly where the reference does (0 * inf): the f32 path may not skip taps."""
+    sw, sh, dw, dh = 384, 216, 128, 72
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3).copy()
+    src[5, 8, 0] = np.inf      # tapped with weight 0 by (dx, dy) = (2, 1): x0 = 7, x1 = 8; y0 = 4, y1 = 5
+    src[100, 200, 1] = np.nan
+    src[215, 383, 2] = -np.inf
+    dst = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev)
+    kb.imgproc.resize(kb.Image(cu(src, dev)), dst, kb.InterpolationMode.Bilinear)
+    assert last_kernel(kb) == "resize_rows_f32_kernel"
+    got, want = dst.numpy(), oracle.resize_f32(src, dw, dh)
+    assert np.isnan(want).any()
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    m = ~np.isnan(want)
+    assert np.array_equal(got[m], want[m])
+
+
+@pytest.mark.parametrize("align", [False, True])
+def test_resize_bilinear_normalize_rows(kb, oracle, dev, align):
+    sw, sh, dw, dh, n = 640, 360, 320, 180, 2
+    src = oracle.pattern_f32(n * sw * sh * 3).reshape(n, sh, sw, 3)
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    dst = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev, batch=n)
+    kb.imgproc.resize_bilinear_normalize(kb.Image(cu(src, dev)), dst, mean, std, align_corners=align)
+    assert last_kernel(kb) == "resize_rows_f32_kernel"
+    if not align:   # (v - mean) * (1/std) on the bilinear sample, cuda/resize.rs:183-235
+        base = np.stack([oracle.resize_f32(src[i], dw, dh) for i in range(n)])
+        inv = (np.float32(1.0) / np.array(std, np.float32))
+        want = (base - np.array(mean, np.float32)) * inv
+        assert_f32_equal(dst.numpy(), want.astype(np.float32), "resize+normalize rows")
+    # both mappings: the staged kernel must equal the gather kernel bit for bit (force the fallback with an odd base)
+    kb._lib.set_knob("rs.npx", 3)
+    again = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev, batch=n)
+    kb.imgproc.resize_bilinear_normalize(kb.Image(cu(src, dev)), again, mean, std, align_corners=align)
+    kb._lib.set_knob("rs.npx", 0)
+    assert torch.equal(again.data, dst.data)
+
+
+def test_full_size_resize_f32_4k(kb, oracle, dev):
+    """The bench's resize_f32 rows at full size: 4K -> 720p / 1080p / 1600x900, whole image against the oracle."""
+    w, h = 3840, 2160
+    src = oracle.pattern_f32(w * h * 3).reshape(h, w, 3)
+    t = kb.Image(cu(src, dev))
+    for dw, dh in ((1280, 720), (1920, 1080), (1600, 900)):
+        dst = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev)
+        kb.imgproc.resize(t, dst, kb.InterpolationMode.Bilinear)
+        assert last_kernel(kb) == "resize_rows_f32_kernel"
+        assert_f32_equal(dst.numpy(), oracle.resize_f32(src, dw, dh), f"4K -> {dw}x{dh}")
