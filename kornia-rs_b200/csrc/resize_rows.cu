@@ -210,6 +210,11 @@ static cudaError_t rr_launch(int mode, unsigned grid, size_t smem, cudaStream_t 
 template <int NPX>
 static int rr_occupancy(int mode, size_t smem) {
     int n = 0;
+    if (smem > 48 * 1024) {   // the occupancy calculator honours the opt-in limit: raise it first
+        cudaError_t a = mode == 2 ? cudaFuncSetAttribute(resize_rows_f32_kernel<NPX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(resize_rows_f32_kernel<NPX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (a != cudaSuccess) { cudaGetLastError(); return 0; }
+    }
     cudaError_t e = mode == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, resize_rows_f32_kernel<NPX, 2>, RR_THREADS, smem)
                               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, resize_rows_f32_kernel<NPX, 1>, RR_THREADS, smem);
     if (e != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -305,7 +305,7 @@ def test_resize_bilinear_normalize_rows(kb, oracle, dev, align):
         inv = (np.float32(1.0) / np.array(std, np.float32))
         want = (base - np.array(mean, np.float32)) * inv
         assert_f32_equal(dst.numpy(), want.astype(np.float32), "resize+normalize rows")
-    # both mappings: the staged kernel must equal the gather kernel bit for bit (force the fallback with an odd base)
+    # both mappings: a different column tiling (3 columns per thread) must give the same bits
     kb._lib.set_knob("rs.npx", 3)
     again = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev, batch=n)
     kb.imgproc.resize_bilinear_normalize(kb.Image(cu(src, dev)), again, mean, std, align_corners=align)
@@ -323,3 +323,91 @@ def test_full_size_resize_f32_4k(kb, oracle, dev):
         kb.imgproc.resize(t, dst, kb.InterpolationMode.Bilinear)
         assert last_kernel(kb) == "resize_rows_f32_kernel"
         assert_f32_equal(dst.numpy(), oracle.resize_f32(src, dw, dh), f"4K -> {dw}x{dh}")
+
+
+# ── warp_stream_kernel (row-streaming, TMA row ring): gentle maps ───────────────
+STREAM_H = [
+    ("cfg5-like", [1.02, 0.03, -7.0, -0.03, 1.01, 4.0, 1.2e-5, 7.0e-6, 1.0]),
+    ("identity", [1, 0, 0, 0, 1, 0, 0, 0, 1]),
+    ("shift", [1, 0, 5.5, 0, 1, -3.25, 0, 0, 1]),
+    ("zoom-out", [0.6, 0.02, 30.0, -0.01, 0.7, 20.0, 0, 0, 1]),        # destination smaller than the source footprint: zero fill around
+    ("zoom-in", [1.8, 0.05, -200.0, 0.04, 1.7, -120.0, 1e-5, 0, 1]),   # rows re-used by several destination rows
+    ("keystone", [1.0, 0.08, -10.0, 0.0, 1.05, -5.0, 0.0, 2.5e-4, 1.0]),
+]
+
+
+@pytest.mark.parametrize("name,h", STREAM_H)
+@pytest.mark.parametrize("mode", ["Bilinear", "Nearest"])
+@pytest.mark.parametrize("size", [(640, 360), (388, 211)])
+def test_warp_perspective_stream(kb, oracle, dev, name, h, mode, size):
+    sw, sh = size
+    n = 2
+    src = oracle.pattern_f32(n * sw * sh * 3).reshape(n, sh, sw, 3)
+    dst = kb.Image.from_size_val(kb.ImageSize(sw, sh), 9.0, 3, torch.float32, dev, batch=n)
+    kb._lib.set_knob("warp.path", 3)
+    try:
+        kb.imgproc.warp_perspective(kb.Image(cu(src, dev)), dst, h, kb.InterpolationMode[mode])
+        k = last_kernel(kb)
+    finally:
+        kb._lib.set_knob("warp.path", 0)
+    assert k == "warp_stream_kernel", k
+    om = oracle.BILINEAR if mode == "Bilinear" else oracle.NEAREST
+    want = np.stack([oracle.warp_perspective_f32(src[i], h, sw, sh, om) for i in range(n)])
+    assert_f32_equal(dst.numpy(), want, f"stream perspective {name} {mode} {size}")
+
+
+@pytest.mark.parametrize("angle,scale", [(0.0, 1.0), (2.0, 1.0), (-3.5, 0.9), (8.0, 1.2), (30.0, 1.0)])
+@pytest.mark.parametrize("mode", ["Bilinear", "Nearest"])
+def test_warp_affine_stream(kb, oracle, dev, angle, scale, mode):
+    """Small rotations stream; 30 degrees has a tall band (forced here: most taps take the resident path through a deep
+    ring or the global fallback — either way the bits must not change)."""
+    sw, sh, dw, dh = 512, 300, 480, 260
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3)
+    m = rot(kb, sw, sh, angle, scale)
+    dst = kb.Image.from_size_val(kb.ImageSize(dw, dh), 9.0, 3, torch.float32, dev)
+    kb._lib.set_knob("warp.path", 3)
+    try:
+        kb.imgproc.warp_affine(kb.Image(cu(src, dev)), dst, m, kb.InterpolationMode[mode])
+        k = last_kernel(kb)
+    finally:
+        kb._lib.set_knob("warp.path", 0)
+    if angle < 20:
+        assert k == "warp_stream_kernel", k
+    om = oracle.BILINEAR if mode == "Bilinear" else oracle.NEAREST
+    assert_f32_equal(dst.numpy(), oracle.warp_affine_f32(src, m, dw, dh, om), f"stream affine {angle} x{scale} {mode} ({k})")
+
+
+def test_warp_stream_small_ring_and_chunks(kb, oracle, dev):
+    """A ring smaller than the band (taps beyond it fall back to global loads), short row chunks (many unit seams) and
+    one column per thread: every knob combination must give the oracle's bits."""
+    sw, sh = 640, 360
+    h = [1.02, 0.06, -7.0, -0.05, 1.01, 9.0, 1.2e-5, 7.0e-6, 1.0]
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3)
+    want = oracle.warp_perspective_f32(src, h, sw, sh, oracle.BILINEAR)
+    t = kb.Image(cu(src, dev))
+    for stages, rc, npx in ((4, 0, 2), (8, 7, 1), (16, 33, 2), (64, 360, 1)):
+        for name, v in (("warp.path", 3), ("ws.stages", stages), ("ws.rc", rc), ("ws.npx", npx)):
+            kb._lib.set_knob(name, v)
+        try:
+            dst = kb.Image.from_size_val(kb.ImageSize(sw, sh), 9.0, 3, torch.float32, dev)
+            kb.imgproc.warp_perspective(t, dst, h, kb.InterpolationMode.Bilinear)
+            assert last_kernel(kb) == "warp_stream_kernel"
+        finally:
+            for name in ("warp.path", "ws.stages", "ws.rc", "ws.npx"):
+                kb._lib.set_knob(name, 0)
+        assert_f32_equal(dst.numpy(), want, f"stream knobs stages={stages} rc={rc} npx={npx}")
+
+
+def test_warp_stream_unaligned_destination(kb, oracle, dev):
+    """dw % 4 != 0: the scalar-store path of the streaming kernel."""
+    sw, sh, dw, dh = 640, 360, 333, 201
+    h = [1.9, 0.03, -3.0, -0.02, 1.8, 2.0, 0.0, 0.0, 1.0]
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3)
+    dst = kb.Image.from_size_val(kb.ImageSize(dw, dh), 9.0, 3, torch.float32, dev)
+    kb._lib.set_knob("warp.path", 3)
+    try:
+        kb.imgproc.warp_perspective(kb.Image(cu(src, dev)), dst, h, kb.InterpolationMode.Bilinear)
+        assert last_kernel(kb) == "warp_stream_kernel"
+    finally:
+        kb._lib.set_knob("warp.path", 0)
+    assert_f32_equal(dst.numpy(), oracle.warp_perspective_f32(src, h, dw, dh, oracle.BILINEAR), "stream unaligned dst")
