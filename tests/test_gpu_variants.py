@@ -350,7 +350,7 @@ def test_warp_perspective_stream(kb, oracle, dev, name, h, mode, size):
         k = last_kernel(kb)
     finally:
         kb._lib.set_knob("warp.path", 0)
-    assert k == "warp_stream_kernel", k
+    assert k == ("warp_stream2_kernel" if mode == "Bilinear" else "warp_stream_kernel"), k
     om = oracle.BILINEAR if mode == "Bilinear" else oracle.NEAREST
     want = np.stack([oracle.warp_perspective_f32(src[i], h, sw, sh, om) for i in range(n)])
     assert_f32_equal(dst.numpy(), want, f"stream perspective {name} {mode} {size}")
@@ -372,7 +372,7 @@ def test_warp_affine_stream(kb, oracle, dev, angle, scale, mode):
     finally:
         kb._lib.set_knob("warp.path", 0)
     if angle < 20:
-        assert k == "warp_stream_kernel", k
+        assert k == ("warp_stream2_kernel" if mode == "Bilinear" else "warp_stream_kernel"), k
     om = oracle.BILINEAR if mode == "Bilinear" else oracle.NEAREST
     assert_f32_equal(dst.numpy(), oracle.warp_affine_f32(src, m, dw, dh, om), f"stream affine {angle} x{scale} {mode} ({k})")
 
@@ -385,13 +385,14 @@ def test_warp_stream_small_ring_and_chunks(kb, oracle, dev):
     src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3)
     want = oracle.warp_perspective_f32(src, h, sw, sh, oracle.BILINEAR)
     t = kb.Image(cu(src, dev))
-    for stages, rc, npx in ((4, 0, 2), (8, 7, 1), (16, 33, 2), (64, 360, 1)):
+    # ws.npx: 1 = pair-row fast consumer (bilinear default), 2 / 3 = generic consumer with two / one columns per thread
+    for stages, rc, npx in ((4, 0, 2), (8, 7, 1), (16, 33, 3), (64, 360, 1), (4, 10, 1), (8, 0, 2)):
         for name, v in (("warp.path", 3), ("ws.stages", stages), ("ws.rc", rc), ("ws.npx", npx)):
             kb._lib.set_knob(name, v)
         try:
             dst = kb.Image.from_size_val(kb.ImageSize(sw, sh), 9.0, 3, torch.float32, dev)
             kb.imgproc.warp_perspective(t, dst, h, kb.InterpolationMode.Bilinear)
-            assert last_kernel(kb) == "warp_stream_kernel"
+            assert last_kernel(kb) == ("warp_stream2_kernel" if npx == 1 else "warp_stream_kernel")
         finally:
             for name in ("warp.path", "ws.stages", "ws.rc", "ws.npx"):
                 kb._lib.set_knob(name, 0)
@@ -407,7 +408,14 @@ def test_warp_stream_unaligned_destination(kb, oracle, dev):
     kb._lib.set_knob("warp.path", 3)
     try:
         kb.imgproc.warp_perspective(kb.Image(cu(src, dev)), dst, h, kb.InterpolationMode.Bilinear)
+        assert last_kernel(kb) == "warp_stream2_kernel"
+        kb._lib.set_knob("ws.npx", 2)
+        dst2 = kb.Image.from_size_val(kb.ImageSize(dw, dh), 9.0, 3, torch.float32, dev)
+        kb.imgproc.warp_perspective(kb.Image(cu(src, dev)), dst2, h, kb.InterpolationMode.Bilinear)
         assert last_kernel(kb) == "warp_stream_kernel"
     finally:
         kb._lib.set_knob("warp.path", 0)
-    assert_f32_equal(dst.numpy(), oracle.warp_perspective_f32(src, h, dw, dh, oracle.BILINEAR), "stream unaligned dst")
+        kb._lib.set_knob("ws.npx", 0)
+    want = oracle.warp_perspective_f32(src, h, dw, dh, oracle.BILINEAR)
+    assert_f32_equal(dst.numpy(), want, "stream2 unaligned dst")
+    assert_f32_equal(dst2.numpy(), want, "stream unaligned dst")
