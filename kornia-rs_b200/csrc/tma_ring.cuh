@@ -34,6 +34,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "TMA_WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Producer-side wait: the producer is normally far ahead and blocked on a full ring, so it must not burn issue slots —
+// try_wait with a suspend-time hint (the warp sleeps until the phase completes or the hint expires).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(2000u) : "memory");
+        if (ok) return;
+    }
+}
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(WS_THREADS) warp_stream_kernel(const float* __
                         }
                         rel_c = max(rel_c, upto);
                         const uint32_t q = qbase + (uint32_t)(r - r0);
-                        tma::mbar_wait(&full_bar[q & smask], (q / P.nslot) & 1u);
+                        tma::mbar_wait(&full_bar[q & smask], (q >> P.nslot_log2) & 1u);
                     }
                     seen = max(seen, ld_i);
                     if (lane == 0) {
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(WS_THREADS) warp_stream_kernel(const float* __
             // `full` phase must complete before the slot is handed back), then release everything still held
             for (int r = seen + 1; r <= ld_c; ++r) {
                 const uint32_t q = qbase + (uint32_t)(r - r0);
-                tma::mbar_wait(&full_bar[q & smask], (q / P.nslot) & 1u);
+                tma::mbar_wait(&full_bar[q & smask], (q >> P.nslot_log2) & 1u);
             }
             __syncwarp();
             if (lane == 0) {
@@ -267,7 +267,9 @@ int launch_warp_stream(cudaStream_t s, const float* src, float* dst, uint32_t sw
     const bool use_fast = BILINEAR && knpx <= 1;
     if (use_fast) knpx = 1;
     if (knpx == 3) knpx = 1;
-    for (int pass = 0; pass < 2 && npx == 0; ++pass) {
+    // default dispatch takes only GENTLE maps (ring <= 64 KB: several CTAs per SM); steeper ones go to the TMA-tiled or gather
+    // kernels (warp.cu) unless the streaming path is forced (knob warp.path = 3: up to a 112 KB ring, then anything)
+    for (int pass = 0; pass < (force == 3 ? 2 : 1) && npx == 0; ++pass) {
         const double cap = (pass == 0 ? 64.0 : 112.0) * 1024.0;
         for (int cand = 2; cand >= 1; --cand) {
             if (knpx >= 1 && knpx <= 2 && cand != knpx) continue;
@@ -281,6 +283,8 @@ int launch_warp_stream(cudaStream_t s, const float* src, float* dst, uint32_t sw
     P.sw = sw; P.sh = sh; P.dw = dw; P.dh = dh;
     for (int i = 0; i < 9; ++i) P.m[i] = (PERSPECTIVE || i < 6) ? minv[i] : 0.0f;
     P.slot_floats = slot; P.row_floats = sw * 3u; P.nslot = nslot;
+    P.nslot_log2 = 0;
+    while ((1u << P.nslot_log2) < nslot) ++P.nslot_log2;
     P.vec_store = ((dw & 3u) == 0 && aligned16(dst)) ? 1u : 0u;
     int per_sm = knob(KNOB_WS_CTAS) > 0 ? knob(KNOB_WS_CTAS) : 4;
     const uint32_t rc = knob(KNOB_WS_RC) > 0 ? (uint32_t)knob(KNOB_WS_RC) : 0u;

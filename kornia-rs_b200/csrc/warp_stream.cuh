@@ -19,6 +19,7 @@ struct WarpStreamParams {
     uint32_t slot_floats;     // floats per ring slot (multiple of 32)
     uint32_t row_floats;      // sw * 3
     uint32_t nslot;           // power of two
+    uint32_t nslot_log2;
     uint32_t vec_store;       // destination rows are 16-byte aligned (dw % 4 == 0, aligned base)
     uint32_t dtx, dcy, dimg;
 };
@@ -173,8 +174,8 @@ __device__ __forceinline__ void ws_producer(const float* __restrict__ src, const
                 // rows ld_c+1 .. ld_last in order; each waits only for its own slot (released in order by the consumers)
                 for (int r = ld_c + 1; r <= ld_last; ++r) {
                     const uint32_t q = qbase + (uint32_t)(r - r0);
-                    const uint32_t slot = q & smask, use = q / P.nslot;
-                    if (use > 0) tma::mbar_wait(&empty_bar[slot], (use - 1u) & 1u);
+                    const uint32_t slot = q & smask, use = q >> P.nslot_log2;
+                    if (use > 0) tma::mbar_wait_backoff(&empty_bar[slot], (use - 1u) & 1u);
                     tma::mbar_expect_tx(&full_bar[slot], bytes);
                     tma::load_1d(ring + (size_t)slot * P.slot_floats, frame + (size_t)r * P.row_floats, bytes, &full_bar[slot]);
                 }

@@ -37,12 +37,15 @@ struct WarpStream2Args {
 };
 
 // Generic (checked) evaluation of one destination pixel: any edge rule, resident or not.  Rare path; never inlined.
+struct Ws2Px { float v0, v1, v2; };
+
 template <bool PERSPECTIVE>
-__device__ __noinline__ void ws2_slow_pixel(const WarpStreamParams& P, const float* __restrict__ gsrc, const float* ring, uint32_t gx, uint32_t dy,
-                                            int rel_g, int ld_g, int c0, int span, uint32_t qoff, float* out) {
-    out[0] = 0.0f; out[1] = 0.0f; out[2] = 0.0f;
+__device__ __noinline__ Ws2Px ws2_slow_pixel(const WarpStreamParams& P, const float* __restrict__ gsrc, const float* ring, uint32_t gx, uint32_t dy,
+                                             int rel_g, int ld_g, int c0, int span, uint32_t qoff) {
+    Ws2Px o;
+    o.v0 = 0.0f; o.v1 = 0.0f; o.v2 = 0.0f;
     float sx, sy;
-    if (!warp_coord<PERSPECTIVE>(P.m, gx, dy, P.sw, P.sh, &sx, &sy)) return;
+    if (!warp_coord<PERSPECTIVE>(P.m, gx, dy, P.sw, P.sh, &sx, &sy)) return o;
     WarpTaps t;
     warp_taps<PERSPECTIVE, true>(sx, sy, P.sw, P.sh, &t);
     const int fa = (int)t.x0 * 3 - c0, fb = (int)t.x1 * 3 - c0;
@@ -52,12 +55,13 @@ __device__ __noinline__ void ws2_slow_pixel(const WarpStreamParams& P, const flo
         const uint32_t smask = P.nslot - 1u;
         const float* ra = ring + (size_t)((qoff + t.y0) & smask) * P.slot_floats;
         const float* rb = ring + (size_t)((qoff + t.y1) & smask) * P.slot_floats;
-        warp_blend<true>(t, ra + fa, ra + fb, rb + fa, rb + fb, &out[0], &out[1], &out[2]);
+        warp_blend<true>(t, ra + fa, ra + fb, rb + fa, rb + fb, &o.v0, &o.v1, &o.v2);
     } else {
         const float* ra = gsrc + (size_t)t.y0 * P.row_floats;
         const float* rb = gsrc + (size_t)t.y1 * P.row_floats;
-        warp_blend_ldg<true>(t, ra + t.x0 * 3u, ra + t.x1 * 3u, rb + t.x0 * 3u, rb + t.x1 * 3u, &out[0], &out[1], &out[2]);
+        warp_blend_ldg<true>(t, ra + t.x0 * 3u, ra + t.x1 * 3u, rb + t.x0 * 3u, rb + t.x1 * 3u, &o.v0, &o.v1, &o.v2);
     }
+    return o;
 }
 
 template <bool PERSPECTIVE>
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(WS_THREADS) warp_stream2_kernel(const float* _
                 const uint32_t yA = yb + i, yB = yA + 1u;
                 const bool b_row = yB < y_end;
                 const int rel_g = __shfl_sync(0xFFFFFFFFu, rel, (int)i), ld_g = __shfl_sync(0xFFFFFFFFu, ld, (int)i);   // identical on both lanes of the pair
-                if (ring_on) {
+                if (ring_on && (ld_g > seen || rel_g > rel_c)) {
                     // bounded-queue discipline (see warp_stream.cu): acquire in order, release in order, release before the
                     // wait that needs the slot back
                     for (int r = seen + 1; r <= ld_g; ++r) {
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(WS_THREADS) warp_stream2_kernel(const float* _
                         }
                         rel_c = max(rel_c, upto);
                         const uint32_t q = qoff + (uint32_t)r;
-                        tma::mbar_wait(&full_bar[q & smask], (q / P.nslot) & 1u);
+                        tma::mbar_wait(&full_bar[q & smask], (q >> P.nslot_log2) & 1u);
                     }
                     seen = max(seen, ld_g);
                     if (lane == 0) {
@@ -213,26 +217,32 @@ __global__ void __launch_bounds__(WS_THREADS) warp_stream2_kernel(const float* _
                 const ws_u64 fxx = ws_fma2(fxp, neg1, one1), fyy = ws_fma2(fyp, neg1, one1);   // 1 - f: one rounding either way
                 const ws_u64 w00 = ws_mul(fxx, fyy, pc), w10 = ws_mul(fxp, fyy, pc), w01 = ws_mul(fxx, fyp, pc), w11 = ws_mul(fxp, fyp, pc);
                 float outA[3], outB[3];
+                // One vote per step: if every lane's two pixels are either out of the image or on the fast path, the step is
+                // straight-line code; a single slow pixel anywhere in the warp sends the whole step through the checked path.
+                const bool lane_fast = (fast[0] || !ok[0]) && (fast[1] || !ok[1]);
+                if (__all_sync(0xFFFFFFFFu, lane_fast)) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    // (x0,y0) (x1,y0) (x0,y1) (x1,y1): immediate offsets 0 / 12 bytes from the two row addresses
-                    const ws_u64 v00 = ws_pack(ws_lds(a0[0] + 4u * c), ws_lds(a0[1] + 4u * c));
-                    const ws_u64 v10 = ws_pack(ws_lds(a0[0] + 12u + 4u * c), ws_lds(a0[1] + 12u + 4u * c));
-                    const ws_u64 v01 = ws_pack(ws_lds(a1[0] + 4u * c), ws_lds(a1[1] + 4u * c));
-                    const ws_u64 v11 = ws_pack(ws_lds(a1[0] + 12u + 4u * c), ws_lds(a1[1] + 12u + 4u * c));
-                    ws_u64 acc = ws_mul(w00, v00, pc);
-                    acc = ws_add(acc, ws_mul(w10, v10, pc), pc);
-                    acc = ws_add(acc, ws_mul(w01, v01, pc), pc);
-                    acc = ws_add(acc, ws_mul(w11, v11, pc), pc);
-                    ws_unpack(acc, outA[c], outB[c]);
-                }
-                if (!fast[0]) {
-                    if (ok[0]) ws2_slow_pixel<PERSPECTIVE>(P, gsrc, ring, gx, yA, ring_on ? rel_g : 0, ring_on ? ld_g : -1, c0, span, qoff, outA);
-                    else { outA[0] = 0.0f; outA[1] = 0.0f; outA[2] = 0.0f; }
-                }
-                if (!fast[1]) {
-                    if (ok[1]) ws2_slow_pixel<PERSPECTIVE>(P, gsrc, ring, gx, yB, ring_on ? rel_g : 0, ring_on ? ld_g : -1, c0, span, qoff, outB);
-                    else { outB[0] = 0.0f; outB[1] = 0.0f; outB[2] = 0.0f; }
+                    for (int c = 0; c < 3; ++c) {
+                        // (x0,y0) (x1,y0) (x0,y1) (x1,y1): immediate offsets 0 / 12 bytes from the two row addresses
+                        const ws_u64 v00 = ws_pack(ws_lds(a0[0] + 4u * c), ws_lds(a0[1] + 4u * c));
+                        const ws_u64 v10 = ws_pack(ws_lds(a0[0] + 12u + 4u * c), ws_lds(a0[1] + 12u + 4u * c));
+                        const ws_u64 v01 = ws_pack(ws_lds(a1[0] + 4u * c), ws_lds(a1[1] + 4u * c));
+                        const ws_u64 v11 = ws_pack(ws_lds(a1[0] + 12u + 4u * c), ws_lds(a1[1] + 12u + 4u * c));
+                        ws_u64 acc = ws_mul(w00, v00, pc);
+                        acc = ws_add(acc, ws_mul(w10, v10, pc), pc);
+                        acc = ws_add(acc, ws_mul(w01, v01, pc), pc);
+                        acc = ws_add(acc, ws_mul(w11, v11, pc), pc);
+                        ws_unpack(acc, outA[c], outB[c]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { outA[c] = ok[0] ? outA[c] : 0.0f; outB[c] = ok[1] ? outB[c] : 0.0f; }
+                } else {
+                    Ws2Px pa, pb;
+                    pa.v0 = pa.v1 = pa.v2 = 0.0f; pb = pa;
+                    if (ok[0]) pa = ws2_slow_pixel<PERSPECTIVE>(P, gsrc, ring, gx, yA, ring_on ? rel_g : 0, ring_on ? ld_g : -1, c0, span, qoff);
+                    if (ok[1]) pb = ws2_slow_pixel<PERSPECTIVE>(P, gsrc, ring, gx, yB, ring_on ? rel_g : 0, ring_on ? ld_g : -1, c0, span, qoff);
+                    outA[0] = pa.v0; outA[1] = pa.v1; outA[2] = pa.v2;
+                    outB[0] = pb.v0; outB[1] = pb.v1; outB[2] = pb.v2;
                 }
                 if (P.vec_store) {
                     float* orow = ws_smem + obuf * OUT_FLOATS + tid * 3u;
@@ -258,7 +268,7 @@ __global__ void __launch_bounds__(WS_THREADS) warp_stream2_kernel(const float* _
         if (r0 >= 0 && staged_unit) {
             for (int r = seen + 1; r <= ld_c; ++r) {
                 const uint32_t q = qoff + (uint32_t)r;
-                tma::mbar_wait(&full_bar[q & smask], (q / P.nslot) & 1u);
+                tma::mbar_wait(&full_bar[q & smask], (q >> P.nslot_log2) & 1u);
             }
             __syncwarp();
             if (lane == 0) {

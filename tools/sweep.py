@@ -55,7 +55,7 @@ if what == "warp":
     ms = timeit(fn)
     print(f"gather   {kb._lib.last_kernel():28s} {ms:.4f} ms  frac {alg / ms / 1e6 / PEAK:.3f}")
     setk(warp_path=3)
-    for npx, stages, ctas, rc in itertools.product((1, 3), (0, 32), (4, 6, 8, 10, 12), (0, 136, 270, 540)):
+    for npx, stages, ctas, rc in itertools.product((1,), (0, 8, 32), (3, 4, 6, 8), (0, 136, 540)):
         setk(ws_npx=npx, ws_stages=stages, ws_ctas=ctas, ws_rc=rc)
         try:
             ms = timeit(fn)
