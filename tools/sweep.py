@@ -52,8 +52,14 @@ if what == "warp":
     fn = lambda: kb.imgproc.warp_perspective(src, dst, H, kb.InterpolationMode.Bilinear)
     alg = n * w * h * 24
     setk(warp_path=1)
-    ms = timeit(fn)
-    print(f"gather   {kb._lib.last_kernel():28s} {ms:.4f} ms  frac {alg / ms / 1e6 / PEAK:.3f}")
+    for a in (1, 0):
+        for pf in (0, 64, 96, 192, 256, -1):
+            setk(a=a, warp_pf=pf)
+            ms = timeit(fn)
+            print(f"gather pf_all={a} pf={pf:3d} {kb._lib.last_kernel():28s} {ms:.4f} ms  frac {alg / ms / 1e6 / PEAK:.3f}", flush=True)
+    setk(a=0, warp_pf=0)
+    if len(sys.argv) > 2 and sys.argv[2] == "gather":
+        sys.exit(0)
     setk(warp_path=3)
     for npx, stages, ctas, rc in itertools.product((1,), (0, 8, 32), (3, 4, 6, 8), (0, 136, 540)):
         setk(ws_npx=npx, ws_stages=stages, ws_ctas=ctas, ws_rc=rc)
