@@ -110,6 +110,17 @@ class RefGpu:
             self.launch(kernel, grid, block, [self._p(src[i]), self._p(dst[i]), C.c_uint(sw), C.c_uint(sh), C.c_uint(dw), C.c_uint(dh),
                                               C.c_float(ax), C.c_float(bx), C.c_float(ay), C.c_float(by)])
 
+    def resize_lanczos(self, src, dst, inter, x0s, wx, y0s, wy):
+        """cuda/resize.rs:823-905 — host-built per-axis tables (lanczos_axis) uploaded by the caller, H pass into the
+        dst_w x src_h intermediate, then V pass; per image."""
+        n, sh, sw, _ = src.shape
+        _, dh, dw, _ = dst.shape
+        gh, bh = self.cfg2d(dw, sh)
+        gv, bv = self.cfg2d(dw, dh)
+        for i in range(n):
+            self.launch("resize_lanczos_h_3c", gh, bh, [self._p(src[i]), self._p(inter), self._p(x0s), self._p(wx), C.c_uint(sw), C.c_uint(sh), C.c_uint(dw)])
+            self.launch("resize_lanczos_v_3c", gv, bv, [self._p(inter), self._p(dst[i]), self._p(y0s), self._p(wy), C.c_uint(sh), C.c_uint(dw), C.c_uint(dh)])
+
     def warp(self, kind: str, interp: str, src, dst, minv):
         """kind 'affine' (6 inverse coefficients) or 'perspective' (9); interp bilinear|nearest|bicubic|lanczos."""
         n, sh, sw, _ = src.shape

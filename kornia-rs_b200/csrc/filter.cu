@@ -453,7 +453,7 @@ static int launch_sep_stream2(cudaStream_t s, const float* src, float* dst, cons
     const int per_sm = tune_ctas > 0 ? tune_ctas : (SOBEL ? 7 : 6);
     const size_t smem = (size_t)P.slot_floats * 4 * stages;
     auto kern = sep_filter_stream2_kernel<C, KX, KY, SOBEL, NV>;
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
     }
@@ -515,7 +515,7 @@ template <int KX, int KY, bool SOBEL>
 static int launch_sep_instance(cudaStream_t s, const float* src, float* dst, const SepTaps& taps, const SepGeom& g,
                                uint32_t batch, size_t smem_bytes) {
     auto kern = sep_filter_fused_kernel<KX, KY, SOBEL>;
-    if (smem_bytes > 48 * 1024) {
+    if (smem_bytes > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem_bytes, cudaGetErrorString(e));
     }

@@ -256,7 +256,7 @@ static int launch_blur_u8(cudaStream_t s, const uint8_t* src, size_t src_len, ui
     const int hx = T.kxn / 2, hy = T.kyn / 2;
     const size_t smem = (size_t)(U8B_TH + 2 * hy) * ((U8B_TW + 2 * hx) * C + U8B_TW * C);
     auto go = [&](auto kern) -> int {
-        if (smem > 48 * 1024) {
+        if (smem > 40 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
         }
@@ -278,7 +278,7 @@ static int launch_blur_u8(cudaStream_t s, const uint8_t* src, size_t src_len, ui
                 const size_t smem_w = (size_t)(U8W_TH + 2 * hx) * (in_ww + mid_ww) * 4;
                 const uint32_t wtx = div_up(cols, U8W_TW), wty = div_up(rows, U8W_TH);
                 const size_t wtiles = (size_t)wtx * wty * batch;
-                if (smem_w > 48 * 1024) {
+                if (smem_w > 40 * 1024) {
                     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
                     if (e != cudaSuccess) return fail(KB200_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu) failed: %s", smem_w, cudaGetErrorString(e));
                 }

@@ -90,7 +90,17 @@ __device__ __forceinline__ void fetch_px(const uint8_t* __restrict__ src, int x,
     }
 }
 
-template <bool F16, bool BILINEAR, bool PTRS>
+// preprocess.rs:481-488 (kernel source): 1-D Lanczos-3 weight — the CUDA math library's sinf, like the reference kernel
+__device__ __forceinline__ float pre_lanczos_w(float dd) {
+    const float ad = fabsf(dd);
+    if (ad < 1e-6f) return 1.0f;
+    if (ad >= 3.0f) return 0.0f;
+    const float pd = 3.14159265358979f * dd;
+    return __fdiv_rn(3.0f * sinf(pd) * sinf(__fdiv_rn(pd, 3.0f)), pd * pd);
+}
+
+// SAMP: kb200_interp — 0 nearest, 1 bilinear, 3 Lanczos-3 (6x6 taps, clamp-to-edge, weights renormalised by their sum)
+template <bool F16, int SAMP, bool PTRS>
 __global__ void __launch_bounds__(256) preprocess_generic_kernel(const __grid_constant__ kb200_preprocess_desc d,
                                                                  const __grid_constant__ PreFrames fr, void* __restrict__ dst,
                                                                  uint32_t frame0) {
@@ -105,7 +115,25 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(const __grid_co
     const bool inside = !(sx < 0.0f || sy < 0.0f || sx >= (float)d.src_w || sy >= (float)d.src_h);
     float px[3];
     if (inside) {
-        if (BILINEAR) {
+        if (SAMP == KB200_INTERP_LANCZOS) {   // preprocess.rs:565-590 sample_lanczos: acc += w * t (unfused), one division per channel
+            const int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+            float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, wsum = 0.0f;
+            for (int j = -2; j <= 3; ++j) {
+                const int yj = y0 + j;
+                const float wy = pre_lanczos_w(sy - (float)yj);
+                const int yc = min(max(yj, 0), d.src_h - 1);
+                for (int ii = -2; ii <= 3; ++ii) {
+                    const int xi = x0 + ii;
+                    const float w = wy * pre_lanczos_w(sx - (float)xi);
+                    const int xc = min(max(xi, 0), d.src_w - 1);
+                    float t[3];
+                    fetch_px(src, xc, yc, d, t);
+                    acc0 += w * t[0]; acc1 += w * t[1]; acc2 += w * t[2];
+                    wsum += w;
+                }
+            }
+            px[0] = __fdiv_rn(acc0, wsum); px[1] = __fdiv_rn(acc1, wsum); px[2] = __fdiv_rn(acc2, wsum);
+        } else if (SAMP == KB200_INTERP_BILINEAR) {
             int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
             const float ax = sx - (float)x0, ay = sy - (float)y0;
             const int x1 = min(x0 + 1, d.src_w - 1), y1 = min(y0 + 1, d.src_h - 1);
@@ -137,7 +165,8 @@ __global__ void __launch_bounds__(256) preprocess_generic_kernel(const __grid_co
         px[0] = d.pad_value; px[1] = d.pad_value; px[2] = d.pad_value;
     }
     float q0, q1, q2;
-    if (inside) { q0 = div255_exact(px[0]); q1 = div255_exact(px[1]); q2 = div255_exact(px[2]); }
+    if (inside && SAMP != KB200_INTERP_LANCZOS) { q0 = div255_exact(px[0]); q1 = div255_exact(px[1]); q2 = div255_exact(px[2]); }
+    else if (inside) { q0 = __fdiv_rn(px[0], 255.0f); q1 = __fdiv_rn(px[1], 255.0f); q2 = __fdiv_rn(px[2], 255.0f); }  // Lanczos overshoots [0, 255]
     else { q0 = __fdiv_rn(px[0], 255.0f); q1 = q0; q2 = q0; }  // pad_value is caller-supplied: plain IEEE division
     const float o0 = (q0 - d.mean[0]) * d.inv_std[0];
     const float o1 = (q1 - d.mean[1]) * d.inv_std[1];
@@ -357,8 +386,8 @@ static int validate_desc(const kb200_preprocess_desc* dp) {
         return fail(KB200_ERR_INVALID_ARGUMENT, "image dimensions must be non-zero");
     if ((long long)d.dst_w * d.dst_h > 0x7FFFFFFFll) return fail(KB200_ERR_DIMS_TOO_LARGE, "dimensions exceed the 32-bit CUDA kernel index limit");  // :1336-1339
     if (d.fmt < 0 || d.fmt > 4) return fail(KB200_ERR_INVALID_ARGUMENT, "unknown source format code %d", d.fmt);
-    if (d.sampling != KB200_INTERP_NEAREST && d.sampling != KB200_INTERP_BILINEAR)
-        return fail(KB200_ERR_UNSUPPORTED, "unsupported sampling mode %d (expected Nearest or Bilinear)", d.sampling);
+    if (d.sampling != KB200_INTERP_NEAREST && d.sampling != KB200_INTERP_BILINEAR && d.sampling != KB200_INTERP_LANCZOS)
+        return fail(KB200_ERR_UNSUPPORTED, "unsupported sampling mode %d (expected Nearest, Bilinear or Lanczos)", d.sampling);  // preprocess.rs:1044-1051
     if (d.fmt <= 1 && d.src_bpp != 3 && d.src_bpp != 4) return fail(KB200_ERR_UNSUPPORTED, "unsupported source channel count %d (expected 3 or 4)", d.src_bpp);
     // SourceFormat::dims_ok :188-195 ; pitch covers a row (PitchedSurface::validate :829-842)
     if (d.fmt == KB200_FMT_NV12 && ((d.src_w | d.src_h) & 1)) return fail(KB200_ERR_INVALID_SOURCE, "invalid raw source for Nv12 at %dx%d (even dimensions required)", d.src_w, d.src_h);
@@ -374,9 +403,10 @@ template <bool F16>
 static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, const uint8_t* const* frames,
                              const uint8_t* base, size_t stride, uint32_t batch, void* dst) {
     const int pixels = d.dst_w * d.dst_h;
-    const bool bil = d.sampling == KB200_INTERP_BILINEAR;
+    const bool bil = d.sampling == KB200_INTERP_BILINEAR, lanczos = d.sampling == KB200_INTERP_LANCZOS;
     // identity fast path: NV12, scale 1, no pad, same size, 8-column vectors possible
-    bool identity = d.fmt == KB200_FMT_NV12 && d.scale_x == 1.0f && d.scale_y == 1.0f && d.pad_x == 0.0f && d.pad_y == 0.0f &&
+    // (Lanczos always takes the generic kernel: its off-centre weights at integer coordinates are sinf(k*pi) != 0 exactly)
+    bool identity = !lanczos && d.fmt == KB200_FMT_NV12 && d.scale_x == 1.0f && d.scale_y == 1.0f && d.pad_x == 0.0f && d.pad_y == 0.0f &&
                     d.dst_w == d.src_w && d.dst_h == d.src_h && (d.src_w % 4) == 0 && aligned16(dst);
     if (identity) {
         if (frames) { for (uint32_t k = 0; k < batch; ++k) identity = identity && ((reinterpret_cast<uintptr_t>(frames[k]) & 3u) == 0); }
@@ -386,7 +416,7 @@ static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, con
     const size_t id_items = (size_t)id_groups * ((size_t)d.src_h / 2);
     if (id_items > 0x7FFFFFFFull) identity = false;
     // NV12 general fast path: vector stores need dst_w % 4 == 0 and a 16-B (f32) / 8-B (f16) aligned destination
-    const bool nv12_fast = d.fmt == KB200_FMT_NV12 && (d.dst_w % 4) == 0 && aligned16(dst) && d.dst_h <= 65535 * NV12_ROWS;
+    const bool nv12_fast = !lanczos && d.fmt == KB200_FMT_NV12 && (d.dst_w % 4) == 0 && aligned16(dst) && d.dst_h <= 65535 * NV12_ROWS;
     Nv12Args nv{};
     nv.groups = (uint32_t)(d.dst_w + 3) / 4u;
     for (int c = 0; c < 3; ++c) nv.pad_norm[c] = (d.pad_value / 255.0f - d.mean[c]) * d.inv_std[c];  // BODY :610-612 on the host (f32, unfused)
@@ -413,11 +443,13 @@ static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, con
         }
         dim3 grid(div_up(pixels, 256), nb);
         if (frames) {
-            if (bil) preprocess_generic_kernel<F16, true, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);
-            else preprocess_generic_kernel<F16, false, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            if (lanczos) preprocess_generic_kernel<F16, KB200_INTERP_LANCZOS, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            else if (bil) preprocess_generic_kernel<F16, KB200_INTERP_BILINEAR, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            else preprocess_generic_kernel<F16, KB200_INTERP_NEAREST, true><<<grid, 256, 0, s>>>(d, fr, dst, f0);
         } else {
-            if (bil) preprocess_generic_kernel<F16, true, false><<<grid, 256, 0, s>>>(d, fr, dst, f0);
-            else preprocess_generic_kernel<F16, false, false><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            if (lanczos) preprocess_generic_kernel<F16, KB200_INTERP_LANCZOS, false><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            else if (bil) preprocess_generic_kernel<F16, KB200_INTERP_BILINEAR, false><<<grid, 256, 0, s>>>(d, fr, dst, f0);
+            else preprocess_generic_kernel<F16, KB200_INTERP_NEAREST, false><<<grid, 256, 0, s>>>(d, fr, dst, f0);
         }
         KB200_TRY(check_launch("preprocess_generic_kernel"));
     }

@@ -477,7 +477,7 @@ static bool axis_weights_all_zero(uint32_t dst_len, uint32_t src_len, float scal
 template <int NPX, int MODE>
 static cudaError_t fr_launch(bool allfma, unsigned grid, size_t smem, cudaStream_t s, const uint8_t* src, float* dst, const FusedRowsParams& R) {
     auto go = [&](auto kern) -> cudaError_t {
-        if (smem > 48 * 1024) {
+        if (smem > 40 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(RR_THREADS) resize_rows_f32_kernel(const float
 template <int NPX>
 static cudaError_t rr_launch(int mode, unsigned grid, size_t smem, cudaStream_t s, const float* src, float* dst, const ResizeRowsParams& P) {
     auto go = [&](auto kern) -> cudaError_t {
-        if (smem > 48 * 1024) {
+        if (smem > 40 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
@@ -210,7 +210,7 @@ static cudaError_t rr_launch(int mode, unsigned grid, size_t smem, cudaStream_t 
 template <int NPX>
 static int rr_occupancy(int mode, size_t smem) {
     int n = 0;
-    if (smem > 48 * 1024) {   // the occupancy calculator honours the opt-in limit: raise it first
+    if (smem > 40 * 1024) {   // the occupancy calculator honours the opt-in limit: raise it first
         cudaError_t a = mode == 2 ? cudaFuncSetAttribute(resize_rows_f32_kernel<NPX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                   : cudaFuncSetAttribute(resize_rows_f32_kernel<NPX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (a != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -184,7 +184,7 @@ static int ws_launch(cudaStream_t s, const float* src, float* dst, WarpStreamPar
     constexpr uint32_t TW = WS_CT * NPX;
     const size_t smem = (size_t)TW * 3u * 4u * 2u + (size_t)P.nslot * P.slot_floats * 4u;
     if (smem > 200 * 1024) return KB200_OK;
-    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return KB200_OK; }
+    if (smem > 40 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return KB200_OK; }
     int resident = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, WS_THREADS, smem) != cudaSuccess || resident < 1) { cudaGetLastError(); return KB200_OK; }
     const int per_sm = std::min(per_sm_want, resident);

@@ -87,7 +87,7 @@ class ImageError(Exception):
 
 
 class InterpolationMode(enum.Enum):
-    """kornia_image::InterpolationMode (image.rs:25).  Bicubic/Lanczos are not on the hot path (SURVEY §8(f))."""
+    """kornia_image::InterpolationMode (image.rs:25)."""
     Nearest = 0
     Bilinear = 1
     Bicubic = 2

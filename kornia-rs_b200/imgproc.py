@@ -23,7 +23,7 @@ from .image import Image, ImageError, ImageSize, InterpolationMode, pair_residen
 LEAF_SCALAR, LEAF_X86_AVX2_FMA, LEAF_AARCH64_NEON = 0, 1, 2
 DEFAULT_LEAF = LEAF_X86_AVX2_FMA
 
-_INTERP = {InterpolationMode.Nearest: 0, InterpolationMode.Bilinear: 1}
+_INTERP = {InterpolationMode.Nearest: 0, InterpolationMode.Bilinear: 1, InterpolationMode.Bicubic: 2, InterpolationMode.Lanczos: 3}
 
 
 def _stream(dev: torch.device) -> int:
@@ -43,7 +43,6 @@ def _prep(op: str, *images: Image) -> torch.device:
 
 def _interp_code(op: str, mode: InterpolationMode) -> int:
     if mode not in _INTERP:
-        # Bicubic / Lanczos exist in the reference but are outside this tier's hot path
         raise ImageError.UnsupportedInterpolation(mode)
     return _INTERP[mode]
 
@@ -72,7 +71,20 @@ def resize(src: Image, dst: Image, interpolation: InterpolationMode) -> None:
     l = _lib.lib()
     args = (_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(),
             src.cols(), src.rows(), dst.cols(), dst.rows())
-    if c == 3 and not (src.size() == dst.size()):
+    if code >= 2:
+        # Bicubic / Lanczos (interpolation/{bicubic,lanczos}.rs): 3-channel device kernels like the reference's
+        # (resize/cuda.rs:40-42); same-size is the reference's copy short-circuit (resize/mod.rs:134-137)
+        if c != 3:
+            raise ImageError.Cuda("CUDA resize supports 3-channel f32 images only; move the images to the host (Image::to_host) to use the CPU path")
+        if src.size() == dst.size():
+            dst.data.copy_(src.data)
+        elif code == 2:
+            _check(l.kb200_resize_bicubic_f32_c3(*args, n))
+        else:
+            need = l.kb200_resize_lanczos_scratch_len(src.rows(), dst.cols(), dst.rows(), n)
+            scratch = torch.empty(need, dtype=torch.float32, device=dev)   # stream-ordered, like the reference's stream.alloc
+            _check(l.kb200_resize_lanczos_f32_c3(args[0], args[1], args[2], args[3], args[4], scratch.data_ptr(), scratch.numel(), *args[5:], n))
+    elif c == 3 and not (src.size() == dst.size()):
         fn = l.kb200_resize_bilinear_f32_c3 if code == 1 else l.kb200_resize_nearest_f32_c3
         _check(fn(*args, n, 0))
     else:

@@ -156,9 +156,6 @@ class PreprocessorBuilder:  # preprocess.rs:654-779
     def _validated(self):
         if self._sampling not in (InterpolationMode.Nearest, InterpolationMode.Bilinear, InterpolationMode.Lanczos):
             raise PreprocessError("UnsupportedSampling", f"unsupported sampling mode {self._sampling!r} (expected Nearest, Bilinear, or Lanczos)")
-        if self._sampling is InterpolationMode.Lanczos:
-            # in the reference; a "next" row here — typed error, never a silent substitute
-            raise PreprocessError("UnsupportedSampling", "Lanczos sampling is not built in this tier (expected Nearest or Bilinear)")
         return self._normalize.mean_inv_std()
 
     def build(self):
@@ -212,7 +209,7 @@ class Preprocessor:
         d.mean = (C.c_float * 3)(*self._mean)
         d.inv_std = (C.c_float * 3)(*self._inv_std)
         d.pad_value = self._pad
-        d.sampling = 0 if self._sampling is InterpolationMode.Nearest else 1
+        d.sampling = {InterpolationMode.Nearest: 0, InterpolationMode.Bilinear: 1, InterpolationMode.Lanczos: 3}[self._sampling]
         return d
 
     @staticmethod

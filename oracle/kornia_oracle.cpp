@@ -212,16 +212,189 @@ static inline float nearest_neighbor_interpolation(const float* img, size_t rows
     return img[(iv * cols + iu) * C + c];
 }
 
-enum { KO_NEAREST = 0, KO_BILINEAR = 1 };
+enum { KO_NEAREST = 0, KO_BILINEAR = 1, KO_BICUBIC = 2, KO_LANCZOS = 3 };
+
+
+// ─────────────────────────────────────────────────────────────────────────────
+// §8(f) #3: bicubic (Keys a = -0.5) and Lanczos-3 samplers — interpolation/bicubic.rs:12-61,
+// interpolation/lanczos.rs:16-266.  The reference keeps these byte-exact with its CUDA kernels: `mul_add` where
+// the kernels say fmaf, plain mul/add elsewhere (this file is built -ffp-contract=off, so plain expressions stay
+// unfused and fmaf() is the only fusion).
+// ─────────────────────────────────────────────────────────────────────────────
+static inline void keys_weights(float frac, float w[4]) {  // bicubic.rs:14-27
+    float t;
+    t = 1.0f + frac; w[0] = fmaf(fmaf(fmaf(-0.5f, t, 2.5f), t, -4.0f), t, 2.0f);
+    t = frac;        w[1] = fmaf(fmaf(1.5f, t, -2.5f) * t, t, 1.0f);
+    t = 1.0f - frac; w[2] = fmaf(fmaf(1.5f, t, -2.5f) * t, t, 1.0f);
+    t = 2.0f - frac; w[3] = fmaf(fmaf(fmaf(-0.5f, t, 2.5f), t, -4.0f), t, 2.0f);
+}
+
+static inline long long clamp_ll(long long v, long long lo, long long hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static inline float bicubic_sample(const float* img, size_t rows, size_t cols, size_t C, float sx, float sy, size_t c) {  // bicubic.rs:33-61
+    const float x0f = floorf(sx), y0f = floorf(sy);
+    float wx[4], wy[4];
+    keys_weights(sx - x0f, wx);
+    keys_weights(sy - y0f, wy);
+    const long long x0 = (long long)x0f, y0 = (long long)y0f;
+    float acc = 0.0f;
+    for (int dy = 0; dy < 4; ++dy) {
+        const size_t yi = (size_t)clamp_ll(y0 + dy - 1, 0, (long long)rows - 1);
+        const size_t row = yi * cols * C;
+        for (int dx = 0; dx < 4; ++dx) {
+            const size_t xi = (size_t)clamp_ll(x0 + dx - 1, 0, (long long)cols - 1);
+            const float w = wx[dx] * wy[dy];
+            acc = fmaf(w, img[row + xi * C + c], acc);
+        }
+    }
+    return acc;
+}
+
+static inline float sin_pi(float x) {  // lanczos.rs:19-35
+    const float k = roundf(x);
+    const float r = x - k;
+    const float z = 3.14159265358979323846f * r;
+    const float z2 = z * z;
+    float p = -2.5052108e-8f;
+    p = p * z2 + 2.7557319e-6f;
+    p = p * z2 + -1.984127e-4f;
+    p = p * z2 + 8.333334e-3f;
+    p = p * z2 + -1.6666667e-1f;
+    const float s = z + z * z2 * p;
+    return (((int)k) & 1) ? -s : s;
+}
+
+static inline float lanczos3(float x) {  // lanczos.rs:39-50
+    const float PI = 3.14159265358979323846f;
+    if (fabsf(x) < 1e-5f) return 1.0f;
+    if (fabsf(x) >= 3.0f) return 0.0f;
+    const float pix = PI * x;
+    const float pix3 = pix * 0.33333334f;
+    return sin_pi(x) * sin_pi(x * (1.0f / 3.0f)) / (pix * pix3);
+}
+
+KO_API float ko_sin_pi(float x) { return sin_pi(x); }
+KO_API float ko_lanczos3(float x) { return lanczos3(x); }
+
+// lanczos.rs:59-92 — per-axis tap base + six normalised weights on the half-pixel grid
+KO_API void ko_lanczos_axis(size_t src_len, size_t dst_len, int32_t* x0s, float* weights) {
+    if (src_len == 0 || dst_len == 0) return;
+    const float a = (float)src_len / (float)dst_len;
+    const float b = 0.5f * a - 0.5f;
+    const float mx = (float)(src_len - 1);
+    for (size_t i = 0; i < dst_len; ++i) {
+        float s = a * (float)i + b;
+        if (s < 0.0f) s = 0.0f;
+        if (s > mx) s = mx;
+        const float x0 = floorf(s);
+        const float frac = s - x0;
+        x0s[i] = (int32_t)x0;
+        float w[6] = {lanczos3(frac + 2.0f), lanczos3(frac + 1.0f), lanczos3(frac), lanczos3(frac - 1.0f), lanczos3(frac - 2.0f), lanczos3(frac - 3.0f)};
+        const float sum = w[0] + w[1] + w[2] + w[3] + w[4] + w[5];
+        const float inv = 1.0f / sum;
+        for (int t = 0; t < 6; ++t) weights[i * 6 + t] = w[t] * inv;
+    }
+}
+
+// lanczos.rs:106-137 — six weights from four sin_pi evaluations (the warp kernels' form)
+KO_API void ko_lanczos3_weights(float frac, float w[6]) {
+    const float PI = 3.14159265358979323846f;
+    const float s = sin_pi(frac);
+    const float t0 = sin_pi(frac * (1.0f / 3.0f));
+    const float t1 = sin_pi((frac - 1.0f) * (1.0f / 3.0f));
+    const float t2 = sin_pi((frac - 2.0f) * (1.0f / 3.0f));
+    const float st0 = s * t0, st1 = s * t1, st2 = s * t2;
+    auto den = [&](float x) { const float pix = PI * x; const float pix3 = pix * 0.33333334f; return pix * pix3; };
+    w[0] = -st1 / den(frac + 2.0f);
+    w[1] = st2 / den(frac + 1.0f);
+    w[2] = st0 / den(frac);
+    w[3] = -st1 / den(frac - 1.0f);
+    w[4] = st2 / den(frac - 2.0f);
+    w[5] = st0 / den(frac - 3.0f);
+    if (frac < 1e-5f) w[2] = 1.0f;
+    if (fabsf(frac - 1.0f) < 1e-5f) w[3] = 1.0f;
+}
+
+static inline float lanczos_sample(const float* img, size_t rows, size_t cols, size_t C, float sx, float sy, size_t c) {  // lanczos.rs:143-181
+    const float x0f = floorf(sx), y0f = floorf(sy);
+    const float frac_x = sx - x0f, frac_y = sy - y0f;
+    const long long x0 = (long long)x0f, y0 = (long long)y0f;
+    float wx[6], wy[6];
+    ko_lanczos3_weights(frac_x, wx);
+    ko_lanczos3_weights(frac_y, wy);
+    const float sum_wx = wx[0] + wx[1] + wx[2] + wx[3] + wx[4] + wx[5];
+    const float sum_wy = wy[0] + wy[1] + wy[2] + wy[3] + wy[4] + wy[5];
+    const float inv_x = 1.0f / sum_wx, inv_y = 1.0f / sum_wy;
+    for (int i = 0; i < 6; ++i) { wx[i] *= inv_x; wy[i] *= inv_y; }
+    float acc = 0.0f;
+    for (int dy = 0; dy < 6; ++dy) {
+        const size_t yi = (size_t)clamp_ll(y0 + dy - 2, 0, (long long)rows - 1);
+        const size_t row = yi * cols * C;
+        float rx = 0.0f;
+        for (int dx = 0; dx < 6; ++dx) {
+            const size_t xi = (size_t)clamp_ll(x0 + dx - 2, 0, (long long)cols - 1);
+            rx = fmaf(wx[dx], img[row + xi * C + c], rx);
+        }
+        acc = fmaf(wy[dy], rx, acc);
+    }
+    return acc;
+}
+
+// lanczos.rs:187-236 — separable H-then-V with an f32 intermediate of dst_w x src_h
+static void resize_lanczos_separable(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh, size_t C) {
+    std::vector<int32_t> x0s(dw), y0s(dh);
+    std::vector<float> wx(dw * 6), wy(dh * 6);
+    ko_lanczos_axis(sw, dw, x0s.data(), wx.data());
+    ko_lanczos_axis(sh, dh, y0s.data(), wy.data());
+    std::vector<float> inter(dw * sh * C);
+#pragma omp parallel for schedule(static)
+    for (long long sy = 0; sy < (long long)sh; ++sy) {
+        const float* srow = src + (size_t)sy * sw * C;
+        float* irow = inter.data() + (size_t)sy * dw * C;
+        for (size_t dx = 0; dx < dw; ++dx) {
+            const long long x0 = x0s[dx];
+            const float* w = &wx[dx * 6];
+            for (size_t k = 0; k < C; ++k) {
+                float acc = 0.0f;
+                for (int t = 0; t < 6; ++t) {
+                    const size_t xi = (size_t)clamp_ll(x0 + t - 2, 0, (long long)sw - 1);
+                    acc = fmaf(w[t], srow[xi * C + k], acc);
+                }
+                irow[dx * C + k] = acc;
+            }
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (long long dy = 0; dy < (long long)dh; ++dy) {
+        const long long y0 = y0s[(size_t)dy];
+        const float* w = &wy[(size_t)dy * 6];
+        float* drow = dst + (size_t)dy * dw * C;
+        for (size_t dx = 0; dx < dw; ++dx)
+            for (size_t k = 0; k < C; ++k) {
+                float acc = 0.0f;
+                for (int t = 0; t < 6; ++t) {
+                    const size_t yi = (size_t)clamp_ll(y0 + t - 2, 0, (long long)sh - 1);
+                    acc = fmaf(w[t], inter[(yi * dw + dx) * C + k], acc);
+                }
+                drow[dx * C + k] = acc;
+            }
+    }
+}
+
+static inline float sample_mode(int mode, const float* img, size_t rows, size_t cols, size_t C, float u, float v, size_t c);
 
 // ─────────────────────────────────────────────────────────────────────────────
 // a1: resize::resize<C>(src,dst,mode) — resize/mod.rs:114-207
 // ─────────────────────────────────────────────────────────────────────────────
 KO_API int ko_resize_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh, size_t C,
                          int mode) {
-    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;
+    if (mode < KO_NEAREST || mode > KO_LANCZOS) return -1;
     if (sw == dw && sh == dh) {  // :134-137
         std::memcpy(dst, src, sw * sh * C * sizeof(float));
+        return 0;
+    }
+    if (mode == KO_LANCZOS) {  // :142-145: separable on both backends
+        resize_lanczos_separable(src, sw, sh, dst, dw, dh, C);
         return 0;
     }
     // axis_lut :169-176 — a*x + b, a = src/dst, b = 0.5a - 0.5, clamp to [0, src-1]
@@ -248,13 +421,21 @@ KO_API int ko_resize_f32(const float* src, size_t sw, size_t sh, float* dst, siz
             for (size_t x = 0; x < dw; ++x) {
                 float* px = dst + (y * dw + x) * C;
                 for (size_t k = 0; k < C; ++k) {
-                    px[k] = (mode == KO_BILINEAR) ? bilinear_interpolation(src, sh, sw, C, xs[x], ys[y], k)
-                                                  : nearest_neighbor_interpolation(src, sh, sw, C, xs[x], ys[y], k);
+                    px[k] = sample_mode(mode, src, sh, sw, C, xs[x], ys[y], k);
                 }
             }
         }
     }
     return 0;
+}
+
+static inline float sample_mode(int mode, const float* img, size_t rows, size_t cols, size_t C, float u, float v, size_t c) {
+    switch (mode) {   // interpolation/interpolate.rs:53-66
+        case KO_BILINEAR: return bilinear_interpolation(img, rows, cols, C, u, v, c);
+        case KO_BICUBIC: return bicubic_sample(img, rows, cols, C, u, v, c);
+        case KO_LANCZOS: return lanczos_sample(img, rows, cols, C, u, v, c);
+        default: return nearest_neighbor_interpolation(img, rows, cols, C, u, v, c);
+    }
 }
 
 // ─────────────────────────────────────────────────────────────────────────────
@@ -595,7 +776,7 @@ KO_API void ko_affine_valid_span(const float axes[6], size_t dst_w, float eps, s
 
 KO_API int ko_warp_affine_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh, size_t C,
                               const float m[6], int mode) {
-    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;
+    if (mode < KO_NEAREST || mode > KO_LANCZOS) return -1;
     float mi[6];
     ko_invert_affine_transform(m, mi);
     const float dsx = mi[0], dsy = mi[3];
@@ -636,7 +817,9 @@ KO_API int ko_warp_affine_f32(const float* src, size_t sw, size_t sh, float* dst
                 const float sx = xstep_x[x] + sx0;
                 const float sy = xstep_y[x] + sy0;
                 float* px = dst_row + x * C;
-                if (mode == KO_NEAREST) {  // :268-272
+                if (mode == KO_BICUBIC || mode == KO_LANCZOS) {  // :325-361: per-pixel samplers on the unclamped coordinate
+                    for (size_t k = 0; k < C; ++k) px[k] = sample_mode(mode, src, sh, sw, C, sx, sy, k);
+                } else if (mode == KO_NEAREST) {  // :268-272
                     float rx = roundf(sx), ry = roundf(sy);
                     rx = std::min(std::max(rx, 0.0f), src_w_f - 1.0f);
                     ry = std::min(std::max(ry, 0.0f), src_h_f - 1.0f);
@@ -829,7 +1012,7 @@ KO_API int ko_remap_u8(const uint8_t* src, size_t sw, size_t sh, uint8_t* dst, s
 
 KO_API int ko_warp_perspective_f32(const float* src, size_t sw, size_t sh, float* dst, size_t dw, size_t dh,
                                    size_t C, const float m[9], int mode) {
-    if (mode != KO_NEAREST && mode != KO_BILINEAR) return -1;
+    if (mode < KO_NEAREST || mode > KO_LANCZOS) return -1;
     float im[9];
     if (ko_invert_homography(m, im) != 0) return -2;  // CannotComputeDeterminant
     const long long nchunks = (long long)((dh + 15) / 16);
@@ -844,9 +1027,7 @@ KO_API int ko_warp_perspective_f32(const float* src, size_t sw, size_t sh, float
                 const float yo = (im[3] * x + im[4] * y + im[5]) / w;
                 if (xo >= 0.0f && xo < (float)sw && yo >= 0.0f && yo < (float)sh) {
                     float* px = dst + (r * dw + c) * C;
-                    for (size_t k = 0; k < C; ++k)
-                        px[k] = (mode == KO_BILINEAR) ? bilinear_interpolation(src, sh, sw, C, xo, yo, k)
-                                                      : nearest_neighbor_interpolation(src, sh, sw, C, xo, yo, k);
+                    for (size_t k = 0; k < C; ++k) px[k] = sample_mode(mode, src, sh, sw, C, xo, yo, k);
                 }
             }
         }
@@ -1261,8 +1442,19 @@ KO_API uint16_t ko_f2h(float f) {
 KO_API int ko_preprocess_frame(const uint8_t* src, void* dst, const ko_preprocess_desc* dp, int out_f16,
                                uint8_t* touched) {
     const ko_preprocess_desc d = *dp;
-    if (d.sampling != KO_NEAREST && d.sampling != KO_BILINEAR) return -1;
+    if (d.sampling != KO_NEAREST && d.sampling != KO_BILINEAR && d.sampling != KO_LANCZOS) return -1;
     const int pixels = d.dst_w * d.dst_h;
+    // preprocess.rs:481-488 (kernel source): 1-D Lanczos-3 weight with libm sinf — the ONE place on this path where
+    // the reference calls a transcendental; host sinf and the CUDA math library may differ in the last ulp, so the
+    // Lanczos preprocess is checked within 1e-4 against this restatement and bit-for-bit against the reference's own
+    // kernel on the GPU (tests/test_ref_gpu_kernels.py).
+    auto lanczos_w = [](float dd) -> float {
+        const float ad = fabsf(dd);
+        if (ad < 1e-6f) return 1.0f;
+        if (ad >= 3.0f) return 0.0f;
+        const float pd = 3.14159265358979f * dd;
+        return 3.0f * sinf(pd) * sinf(pd / 3.0f) / (pd * pd);
+    };
     float* dst32 = (float*)dst;
     uint16_t* dst16 = (uint16_t*)dst;
     auto mark = [&](int x, int y) {
@@ -1300,6 +1492,26 @@ KO_API int ko_preprocess_frame(const uint8_t* src, void* dst, const ko_preproces
                     const float bot = t01[c] + (t11[c] - t01[c]) * ax;
                     px[c] = top + (bot - top) * ay;
                 }
+            } else if (d.sampling == KO_LANCZOS) {  // :565-590 sample_lanczos
+                const int x0 = (int)floorf(sx), y0 = (int)floorf(sy);
+                float acc[3] = {0.0f, 0.0f, 0.0f};
+                float wsum = 0.0f;
+                for (int j = -2; j <= 3; ++j) {
+                    const int yj = y0 + j;
+                    const float wyv = lanczos_w(sy - (float)yj);
+                    const int yc = std::min(std::max(yj, 0), d.src_h - 1);
+                    for (int ii = -2; ii <= 3; ++ii) {
+                        const int xi = x0 + ii;
+                        const float w = wyv * lanczos_w(sx - (float)xi);
+                        const int xc = std::min(std::max(xi, 0), d.src_w - 1);
+                        float t[3];
+                        fetch_px(src, xc, yc, d, t);
+                        mark(xc, yc);
+                        for (int c = 0; c < 3; ++c) acc[c] += w * t[c];
+                        wsum += w;
+                    }
+                }
+                px[0] = acc[0] / wsum; px[1] = acc[1] / wsum; px[2] = acc[2] / wsum;
             } else {  // :556-563
                 const int xn = std::min(std::max((int)roundf(sx), 0), d.src_w - 1);
                 const int yn = std::min(std::max((int)roundf(sy), 0), d.src_h - 1);

@@ -19,7 +19,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libkornia_oracle.so")
 
-NEAREST, BILINEAR = 0, 1
+NEAREST, BILINEAR, BICUBIC, LANCZOS = 0, 1, 2, 3
 LEAF_SCALAR, LEAF_X86, LEAF_NEON = 0, 1, 2
 LETTERBOX, STRETCH = 0, 1
 FMT_RGB, FMT_BGR, FMT_GRAY, FMT_NV12, FMT_YUYV = 0, 1, 2, 3, 4
@@ -110,6 +110,10 @@ def _declare(l: C.CDLL) -> None:
     l.ko_preprocess_cpu_rgb_bilinear.argtypes = [vp, sz, sz, vp, sz, sz, i, vp, vp, f, i]
     l.ko_count_touched_resize.argtypes = [sz, sz, sz, sz, i]
     l.ko_count_touched_resize.restype = sz
+    l.ko_sin_pi.argtypes = [C.c_float]; l.ko_sin_pi.restype = C.c_float
+    l.ko_lanczos3.argtypes = [C.c_float]; l.ko_lanczos3.restype = C.c_float
+    l.ko_lanczos_axis.argtypes = [sz, sz, vp, vp]; l.ko_lanczos_axis.restype = None
+    l.ko_lanczos3_weights.argtypes = [C.c_float, vp]; l.ko_lanczos3_weights.restype = None
     l.ko_set_threads.argtypes = [i]
     l.ko_max_threads.restype = i
 
@@ -538,3 +542,24 @@ def nv12_from_rgb(src: np.ndarray) -> np.ndarray:
     if lib().ko_nv12_from_rgb_u8(_p(src), w, h, _p(dst)) != 0:
         raise ValueError("InvalidImageSize")
     return dst
+
+
+# ── bicubic / Lanczos ──────────────────────────────────────
+def sin_pi(x: float) -> float:
+    return float(lib().ko_sin_pi(float(x)))
+
+
+def lanczos3(x: float) -> float:
+    return float(lib().ko_lanczos3(float(x)))
+
+
+def lanczos3_weights(frac: float) -> np.ndarray:
+    w = np.empty(6, np.float32)
+    lib().ko_lanczos3_weights(float(frac), _p(w))
+    return w
+
+
+def lanczos_axis(src_len: int, dst_len: int):
+    x0s, w = np.empty(dst_len, np.int32), np.empty(dst_len * 6, np.float32)
+    lib().ko_lanczos_axis(src_len, dst_len, _p(x0s), _p(w))
+    return x0s, w.reshape(dst_len, 6)

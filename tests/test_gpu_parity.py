@@ -494,8 +494,8 @@ def test_warp_errors(kb, oracle, dev):
     dst = kb.Image.zeros_cuda(kb.ImageSize(8, 8), 3, torch.float32, dev)
     with pytest.raises(kb.ImageError, match="singular"):
         kb.imgproc.warp_perspective(src, dst, [1, 2, 3, 2, 4, 6, 3, 6, 9], kb.InterpolationMode.Bilinear)
-    with pytest.raises(kb.ImageError, match="Unsupported interpolation"):
-        kb.imgproc.warp_affine(src, dst, [1, 0, 0, 0, 1, 0], kb.InterpolationMode.Bicubic)
+    for mode in (kb.InterpolationMode.Bicubic, kb.InterpolationMode.Lanczos):   # warp/affine.rs:528-550: all modes are supported
+        kb.imgproc.warp_affine(src, dst, [1, 0, 0, 0, 1, 0], mode)
     gray = kb.Image.zeros_cuda(kb.ImageSize(8, 8), 1, torch.float32, dev)
     with pytest.raises(kb.ImageError, match="3-channel f32 images only"):
         kb.imgproc.warp_affine(gray, gray, [1, 0, 0, 0, 1, 0], kb.InterpolationMode.Bilinear)

@@ -419,3 +419,57 @@ def test_warp_stream_unaligned_destination(kb, oracle, dev):
     want = oracle.warp_perspective_f32(src, h, dw, dh, oracle.BILINEAR)
     assert_f32_equal(dst.numpy(), want, "stream2 unaligned dst")
     assert_f32_equal(dst2.numpy(), want, "stream unaligned dst")
+
+
+# ── bicubic / Lanczos samplers against the oracle ──────────────
+HQ = [("Bicubic", 2), ("Lanczos", 3)]
+
+
+@pytest.mark.parametrize("name,code", HQ)
+@pytest.mark.parametrize("sw,sh,dw,dh", [(129, 97, 64, 48), (64, 48, 129, 97), (258, 195, 128, 128), (31, 17, 7, 5), (5, 7, 31, 17), (640, 360, 213, 120)])
+def test_resize_hq(kb, oracle, dev, name, code, sw, sh, dw, dh):
+    n = 2
+    src = oracle.pattern_f32(n * sw * sh * 3).reshape(n, sh, sw, 3)
+    dst = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev, batch=n)
+    kb.imgproc.resize(kb.Image(cu(src, dev)), dst, kb.InterpolationMode[name])
+    want = np.stack([oracle.resize_f32(src[i], dw, dh, code) for i in range(n)])
+    assert_f32_equal(dst.numpy(), want, f"resize {name} {sw}x{sh}->{dw}x{dh}")
+
+
+@pytest.mark.parametrize("name,code", HQ)
+def test_warps_hq(kb, oracle, dev, name, code):
+    sw, sh, dw, dh = 97, 61, 80, 70
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3)
+    for angle in (0.0, 30.0, 90.0, -17.5):
+        m = rot(kb, sw, sh, angle, 0.9)
+        dst = kb.Image.from_size_val(kb.ImageSize(dw, dh), 4.0, 3, torch.float32, dev)
+        kb.imgproc.warp_affine(kb.Image(cu(src, dev)), dst, m, kb.InterpolationMode[name])
+        assert_f32_equal(dst.numpy(), oracle.warp_affine_f32(src, m, dw, dh, code), f"warp_affine {name} {angle}")
+    for h in ([1.03, 0.05, -3.0, -0.02, 0.97, 4.0, 2.0 / (97 * 129), 1.5 / (129 * 97), 1.0], [0.9, 0.15, 10.0, -0.1, 1.1, -6.0, 0.0, 0.0, 1.0]):
+        dst = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev)   # CPU leaves OOB untouched, GPU writes 0
+        kb.imgproc.warp_perspective(kb.Image(cu(src, dev)), dst, h, kb.InterpolationMode[name])
+        assert_f32_equal(dst.numpy(), oracle.warp_perspective_f32(src, h, dw, dh, code), f"warp_perspective {name}")
+    gray = kb.Image.zeros_cuda(kb.ImageSize(8, 8), 1, torch.float32, dev)
+    with pytest.raises(kb.ImageError, match="3-channel f32 images only"):
+        kb.imgproc.resize(gray, kb.Image.zeros_cuda(kb.ImageSize(4, 4), 1, torch.float32, dev), kb.InterpolationMode[name])
+
+
+@pytest.mark.parametrize("fmt,bpp", [("Rgb8", 3), ("Nv12", 1), ("Yuyv", 2), ("Gray8", 1)])
+@pytest.mark.parametrize("f16", [False, True])
+def test_preprocess_lanczos_vs_oracle(kb, oracle, dev, fmt, bpp, f16):
+    """Lanczos sampling of the camera preprocess: the reference kernel calls sinf (CUDA math library); the oracle calls
+    host sinf — checked within the north-star tolerance (1e-4 on [0,1]-scaled values); bit-equality with the reference's
+    own kernel is asserted in test_ref_gpu_kernels.py."""
+    w, h, dw, dh, n = 96, 64, 50, 40, 2
+    nbytes = {"Rgb8": w * h * 3, "Nv12": w * h * 3 // 2, "Yuyv": w * h * 2, "Gray8": w * h}[fmt]
+    raws = [oracle.pattern_u8(nbytes, 900 + k) for k in range(n)]
+    pre = (kb.Preprocessor.builder().source_format(kb.SourceFormat[fmt]).mode(kb.ResizeMode.Letterbox).sampling(kb.InterpolationMode.Lanczos)
+           .normalize(kb.Normalize.UnitScale()).build_cuda())
+    dst = torch.zeros((n, 3, dh, dw), dtype=torch.float16 if f16 else torch.float32, device=dev)
+    (pre.run_raw_batch_f16 if f16 else pre.run_raw_batch)([cu(r, dev) for r in raws], w, h, dst)
+    code = {"Rgb8": oracle.FMT_RGB, "Nv12": oracle.FMT_NV12, "Yuyv": oracle.FMT_YUYV, "Gray8": oracle.FMT_GRAY}[fmt]
+    cfg = oracle.PreprocessCfg(mode=oracle.LETTERBOX, fmt=code, sampling=oracle.LANCZOS)
+    want = np.stack([oracle.preprocess_frame(r, cfg, w, h, dw, dh) for r in raws])
+    got = dst.float().cpu().numpy()
+    tol = 2e-3 if f16 else 1e-4
+    assert np.max(np.abs(got - want)) <= tol, np.max(np.abs(got - want))

@@ -797,3 +797,85 @@ def test_video_encode_reference_known_answers(oracle):
     np.testing.assert_array_equal(uv[..., 1], ev(qa(R), qa(G), qa(B)))
     with pytest.raises(ValueError):
         oracle.nv12_from_rgb(np.zeros((5, 4, 3), np.uint8))
+
+
+# ── bicubic / Lanczos samplers ──────────────────────────────
+def test_lanczos_four_eval_weights_match_per_tap_form(oracle):
+    """interpolation/lanczos.rs:242-265 `four_eval_weights_match_per_tap_form`: the 4-sin_pi weight path agrees with the
+    per-tap lanczos3 to 1e-6 over the whole frac range; exact edge values w0[2] == 1, w0[5] == 0."""
+    for i in range(0, 10001, 7):
+        frac = np.float32(i) / np.float32(10001.0)
+        w = oracle.lanczos3_weights(frac)
+        per_tap = [oracle.lanczos3(np.float32(frac) + np.float32(o)) for o in (2.0, 1.0, 0.0, -1.0, -2.0, -3.0)]
+        assert np.max(np.abs(w - np.array(per_tap, np.float32))) < 1e-6, frac
+    w0 = oracle.lanczos3_weights(0.0)
+    assert w0[2] == 1.0 and w0[5] == 0.0
+
+
+def test_sin_pi_and_lanczos_axis_properties(oracle):
+    """sin_pi (lanczos.rs:19-35) against libm in f64; lanczos_axis rows are normalised and centred on the tap base."""
+    for x in np.linspace(-3.0, 3.0, 601):
+        assert abs(oracle.sin_pi(np.float32(x)) - np.sin(np.pi * float(np.float32(x)))) < 5e-7
+    x0s, w = oracle.lanczos_axis(97, 40)
+    assert x0s.shape == (40,) and w.shape == (40, 6)
+    assert np.all(np.abs(w.sum(axis=1) - 1.0) < 1e-6)
+    a = np.float32(97) / np.float32(40)
+    s = np.clip(a * np.arange(40, dtype=np.float32) + (np.float32(0.5) * a - np.float32(0.5)), 0, 96)
+    assert np.array_equal(x0s, np.floor(s).astype(np.int32))
+
+
+def _keys_f64(t):
+    t = abs(t)
+    if t <= 1:
+        return 1.5 * t ** 3 - 2.5 * t ** 2 + 1
+    if t < 2:
+        return -0.5 * t ** 3 + 2.5 * t ** 2 - 4 * t + 2
+    return 0.0
+
+
+def test_bicubic_resize_against_f64_restatement(oracle):
+    """resize Bicubic (resize/mod.rs:197 -> interpolation/bicubic.rs:33-61) against an independent f64 Keys a=-0.5
+    implementation on the same half-pixel grid with replicate-clamped taps; and exactness on constant / linear ramps."""
+    sw, sh, dw, dh, c = 23, 17, 31, 11, 3
+    src = oracle.pattern_f32(sw * sh * c).reshape(sh, sw, c)
+    got = oracle.resize_f32(src, dw, dh, oracle.BICUBIC)
+    want = np.zeros((dh, dw, c))
+    ax, ay = np.float32(sw) / np.float32(dw), np.float32(sh) / np.float32(dh)
+    for y in range(dh):
+        sy = float(np.clip(ay * np.float32(y) + (np.float32(0.5) * ay - np.float32(0.5)), 0, sh - 1))
+        y0 = int(np.floor(sy))
+        for x in range(dw):
+            sx = float(np.clip(ax * np.float32(x) + (np.float32(0.5) * ax - np.float32(0.5)), 0, sw - 1))
+            x0 = int(np.floor(sx))
+            acc = np.zeros(c)
+            for j in range(-1, 3):
+                for i in range(-1, 3):
+                    acc += _keys_f64(sx - (x0 + i)) * _keys_f64(sy - (y0 + j)) * src[min(max(y0 + j, 0), sh - 1), min(max(x0 + i, 0), sw - 1)]
+            want[y, x] = acc
+    assert np.max(np.abs(got - want)) < 2e-6
+    const = np.full((9, 12, 1), 0.375, np.float32)
+    assert np.max(np.abs(oracle.resize_f32(const, 20, 15, oracle.BICUBIC) - 0.375)) < 1e-6     # weights sum to 1
+    assert np.max(np.abs(oracle.resize_f32(const, 5, 4, oracle.LANCZOS) - 0.375)) < 1e-6
+
+
+def test_warps_support_all_modes_identity(oracle):
+    """warp/affine.rs:528-550 `warp_affine_supports_all_modes`, warp/perspective.rs:475-496: identity warps succeed in
+    every mode; on integer coordinates bicubic reproduces the source exactly (Keys weights are 0,1,0,0 at frac 0)."""
+    src = oracle.pattern_f32(8 * 6 * 3).reshape(6, 8, 3)
+    for mode in (oracle.NEAREST, oracle.BILINEAR, oracle.BICUBIC):
+        assert np.array_equal(oracle.warp_affine_f32(src, [1, 0, 0, 0, 1, 0], 8, 6, mode), src)
+        assert np.array_equal(oracle.warp_perspective_f32(src, [1, 0, 0, 0, 1, 0, 0, 0, 1], 8, 6, mode), src)
+    lz = oracle.warp_affine_f32(src, [1, 0, 0, 0, 1, 0], 8, 6, oracle.LANCZOS)
+    assert np.max(np.abs(lz - src)) < 1e-6      # w[2] = 1 exactly, the other taps are sin_pi(0) * ... = 0, renormalised by 1
+
+
+def test_preprocess_lanczos_solid_and_bounds(oracle):
+    """preprocess.rs sample_lanczos (kernel source :565-590): a solid frame stays solid (weights renormalised by their
+    sum); letterbox pad pixels keep the pad value."""
+    w, h = 32, 24
+    src = np.full((h, w, 3), 200, np.uint8)
+    cfg = oracle.PreprocessCfg(mode=oracle.LETTERBOX, fmt=oracle.FMT_RGB, mean=(0.0, 0.0, 0.0), inv_std=(1.0, 1.0, 1.0), sampling=oracle.LANCZOS)
+    out = oracle.preprocess_frame(src.reshape(-1), cfg, w, h, 20, 20)
+    inside = out[:, 3:17, :]
+    assert np.max(np.abs(inside - np.float32(200.0) / np.float32(255.0))) < 1e-5
+    assert np.all(out[:, 0, :] == np.float32(114.0) / np.float32(255.0))

@@ -157,3 +157,65 @@ def test_preprocess_nv12_matches_reference_kernel(kb, oracle, ref, dev, mode, dw
         assert torch.equal(got.view(torch.int16), want.view(torch.int16))
     else:
         same_bits(got, want, f"preprocess {mode} {dw}x{dh}")
+
+
+# ── bicubic / Lanczos: the reference's own kernels are the byte-exact spec (interpolation/bicubic.rs:1-8) ──────
+@pytest.mark.parametrize("sw,sh,dw,dh", [(129, 97, 64, 48), (64, 48, 129, 97), (320, 180, 213, 120), (40, 30, 40, 77)])
+def test_resize_bicubic_and_lanczos_match_reference_kernels(kb, oracle, ref, dev, sw, sh, dw, dh):
+    n = 2
+    src = cu(oracle.pattern_f32(n * sw * sh * 3).reshape(n, sh, sw, 3), dev)
+    want = torch.zeros((n, dh, dw, 3), dtype=torch.float32, device=dev)
+    ref.resize_bilinear(src, want, kernel="resize_bicubic_3c")
+    got = kb.Image.zeros_cuda(kb.ImageSize(dw, dh), 3, torch.float32, dev, batch=n)
+    kb.imgproc.resize(kb.Image(src), got, kb.InterpolationMode.Bicubic)
+    same_bits(got.data, want, f"bicubic {sw}x{sh}->{dw}x{dh}")
+    x0s, wx = oracle.lanczos_axis(sw, dw)
+    y0s, wy = oracle.lanczos_axis(sh, dh)
+    inter = torch.zeros((sh, dw, 3), dtype=torch.float32, device=dev)
+    ref.resize_lanczos(src, want, inter, cu(x0s, dev), cu(wx, dev), cu(y0s, dev), cu(wy, dev))
+    kb.imgproc.resize(kb.Image(src), got, kb.InterpolationMode.Lanczos)
+    same_bits(got.data, want, f"lanczos {sw}x{sh}->{dw}x{dh}")
+
+
+@pytest.mark.parametrize("interp", ["bicubic", "lanczos"])
+@pytest.mark.parametrize("size,h", H_CASES)
+def test_warp_perspective_hq_matches_reference_kernel(kb, oracle, ref, dev, size, h, interp):
+    sw, sh = size
+    src = cu(oracle.pattern_f32(sw * sh * 3).reshape(1, sh, sw, 3), dev)
+    want = torch.full((1, sh, sw, 3), 3.0, dtype=torch.float32, device=dev)
+    ref.warp("perspective", interp, src, want, oracle.invert_homography(h))
+    got = kb.Image.from_size_val(kb.ImageSize(sw, sh), 3.0, 3, torch.float32, dev)
+    kb.imgproc.warp_perspective(kb.Image(src[0]), got, h, kb.InterpolationMode.Bicubic if interp == "bicubic" else kb.InterpolationMode.Lanczos)
+    same_bits(got.data.reshape(want.shape), want, f"warp_perspective {interp} {size}")
+
+
+@pytest.mark.parametrize("interp", ["bicubic", "lanczos"])
+@pytest.mark.parametrize("size,angle", [((128, 96), 30.0), ((97, 61), 90.0), ((256, 192), -17.5)])
+def test_warp_affine_hq_matches_reference_kernel(kb, oracle, ref, dev, size, angle, interp):
+    sw, sh = size
+    src = cu(oracle.pattern_f32(sw * sh * 3).reshape(1, sh, sw, 3), dev)
+    m = kb.imgproc.get_rotation_matrix2d((sw / 2.0, sh / 2.0), angle, 1.0)
+    want = torch.full((1, sh, sw, 3), 3.0, dtype=torch.float32, device=dev)
+    ref.warp("affine", interp, src, want, oracle.invert_affine_transform(m))
+    got = kb.Image.from_size_val(kb.ImageSize(sw, sh), 3.0, 3, torch.float32, dev)
+    kb.imgproc.warp_affine(kb.Image(src[0]), got, m, kb.InterpolationMode.Bicubic if interp == "bicubic" else kb.InterpolationMode.Lanczos)
+    same_bits(got.data.reshape(want.shape), want, f"warp_affine {interp} {size} {angle}")
+
+
+@pytest.mark.parametrize("mode,dw,dh", [("Letterbox", 64, 64), ("Stretch", 77, 41), ("Stretch", 300, 200)])
+@pytest.mark.parametrize("fmt", ["Nv12", "Rgb8"])
+def test_preprocess_lanczos_matches_reference_kernel(kb, oracle, ref, dev, mode, dw, dh, fmt):
+    """sample_lanczos (preprocess.rs:565-590) uses the CUDA math library's sinf: the reference's kernel, run here, is the
+    bit spec; the C++ oracle (host sinf) is checked within the 1e-4 tolerance in test_gpu_variants.py."""
+    w, h, n = 192, 108, 2
+    nbytes = w * h * 3 // 2 if fmt == "Nv12" else w * h * 3
+    frames = [cu(raw_bytes(nbytes, k), dev) for k in range(n)]
+    inv = [float(np.float32(1.0) / np.float32(s)) for s in kb.IMAGENET_STD]
+    aff = oracle.preprocess_affine(oracle.LETTERBOX if mode == "Letterbox" else oracle.STRETCH, w, h, dw, dh)
+    want = torch.zeros((n, 3, dh, dw), dtype=torch.float32, device=dev)
+    ref.preprocess(frames, w, h, want, aff, kb.IMAGENET_MEAN, inv, 114.0, fmt=3 if fmt == "Nv12" else 0, bpp=1 if fmt == "Nv12" else 3, sampler="lanczos")
+    pre = (kb.Preprocessor.builder().source_format(kb.SourceFormat[fmt]).mode(kb.ResizeMode[mode]).sampling(kb.InterpolationMode.Lanczos)
+           .normalize(kb.Normalize.imagenet()).build_cuda())
+    got = torch.zeros_like(want)
+    pre.run_raw_batch(frames, w, h, got)
+    same_bits(got, want, f"preprocess lanczos {fmt} {mode} {dw}x{dh}")
