@@ -119,7 +119,7 @@ class RefGpu:
         gv, bv = self.cfg2d(dw, dh)
         for i in range(n):
             self.launch("resize_lanczos_h_3c", gh, bh, [self._p(src[i]), self._p(inter), self._p(x0s), self._p(wx), C.c_uint(sw), C.c_uint(sh), C.c_uint(dw)])
-            self.launch("resize_lanczos_v_3c", gv, bv, [self._p(inter), self._p(dst[i]), self._p(y0s), self._p(wy), C.c_uint(sh), C.c_uint(dw), C.c_uint(dh)])
+            self.launch("resize_lanczos_v_3c", gv, bv, [self._p(inter), self._p(dst[i]), self._p(y0s), self._p(wy), C.c_uint(dw), C.c_uint(sh), C.c_uint(dh)])
 
     def warp(self, kind: str, interp: str, src, dst, minv):
         """kind 'affine' (6 inverse coefficients) or 'perspective' (9); interp bilinear|nearest|bicubic|lanczos."""

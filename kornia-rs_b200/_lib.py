@@ -50,6 +50,10 @@ def _declare(l: C.CDLL) -> None:
         "kb200_resize_bicubic_f32_c3": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32], i),
         "kb200_resize_lanczos_scratch_len": ([u32, u32, u32, u32], sz),
         "kb200_resize_lanczos_f32_c3": ([vp, vp, sz, vp, sz, vp, sz, u32, u32, u32, u32, u32], i),
+        "kb200_pyrdown_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32], i),
+        "kb200_pyrup_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32], i),
+        "kb200_pyrdown_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32], i),
+        "kb200_pyrup_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32], i),
         "kb200_resize_normalize_chw_u8_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, fp, i], i),
         "kb200_resize_row_plan": ([u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)], None),
         "kb200_resize_normalize_chw_u8_f32_rows": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, fp, fp, i, u32, u32, u32], i),

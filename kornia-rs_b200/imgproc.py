@@ -647,3 +647,40 @@ def std_mean(image: Image) -> tuple[list[float], list[float]]:
     """core.rs:42 `std_mean(&Image<u8,3>) -> (std, mean)` (synchronises to return host f64s)."""
     sums = std_mean_sums(image).tolist()
     return std_mean_finalize(sums, image.rows() * image.cols() * image.batch)
+
+
+# ── Gaussian pyramids (pyramid.rs) ───────────────────────────────────────────
+def _pyr(op: str, src: Image, dst: Image, up: bool) -> None:
+    dev = _prep(op, src, dst)
+    if src.dtype not in (torch.float32, torch.uint8) or dst.dtype != src.dtype:
+        raise ImageError.DtypeMismatch("f32 or u8, equal on both sides", (src.dtype, dst.dtype))
+    c = src.num_channels()
+    if dst.num_channels() != c:
+        raise ImageError.InvalidChannelShape(dst.num_channels(), c)
+    ew, eh = (src.cols() * 2, src.rows() * 2) if up else ((src.cols() + 1) // 2, (src.rows() + 1) // 2)
+    if dst.cols() != ew or dst.rows() != eh:   # pyramid.rs:217-225 / :319-327
+        raise ImageError.InvalidImageSize(ew, eh, dst.cols(), dst.rows())
+    n = _same_batch(src, dst)
+    name = f"kb200_pyr{'up' if up else 'down'}_{'f32' if src.dtype == torch.float32 else 'u8'}"
+    _check(getattr(_lib.lib(), name)(_stream(dev), src.data.data_ptr(), src.numel(), dst.data.data_ptr(), dst.numel(), src.cols(), src.rows(), c, n))
+
+
+def pyrdown(src: Image, dst: Image) -> None:
+    """pyramid.rs:312 `pyrdown_f32` / :469 `pyrdown_u8` — 5x5 Gaussian + 2x decimation, BORDER_REFLECT_101; dst = ceil(src / 2)."""
+    _pyr("pyrdown", src, dst, False)
+
+
+def pyrup(src: Image, dst: Image) -> None:
+    """pyramid.rs:210 `pyrup_f32` / :804 `pyrup_u8` — 2x polyphase upsampling; dst = 2 * src."""
+    _pyr("pyrup", src, dst, True)
+
+
+def build_pyramid(src: Image, max_level: int) -> list[Image]:
+    """pyramid.rs:431 `build_pyramid` — [src, pyrdown(src), ...] with max_level + 1 entries (level sizes by div_ceil)."""
+    levels = [src]
+    for _ in range(max_level):
+        cur = levels[-1]
+        nxt = Image.zeros_cuda(ImageSize((cur.cols() + 1) // 2, (cur.rows() + 1) // 2), cur.num_channels(), cur.dtype, cur.device, batch=cur.batch)
+        pyrdown(cur, nxt)
+        levels.append(nxt)
+    return levels

@@ -1590,3 +1590,146 @@ KO_API size_t ko_count_touched_resize(size_t sw, size_t sh, size_t dw, size_t dh
     for (auto v : ty) ny += v;
     return nx * ny;
 }
+
+// ─────────────────────────────────────────────────────────────────────────────
+// §8(f) #4: Gaussian pyramids — pyramid.rs:22-250 (pyrup_f32: polyphase [1,4,6,4,1]/8 with its own border
+// rule), :252-427 (reflect_101, pyrdown_f32: 25 taps `sum += v * (ky*kx)` unfused, BORDER_REFLECT_101),
+// :469-650 (pyrdown_u8: u16 horizontal sums, (sum + 128) >> 8), :656-840 (pyrup_u8: (p + 6c + n + 4) >> 3 /
+// (c + n + 1) >> 1 with reflect_101 neighbours).
+// ─────────────────────────────────────────────────────────────────────────────
+static inline int reflect_101(int p, int len) {  // pyramid.rs:252-269
+    if (len == 1) return 0;
+    if (p < 0) p = -p;
+    const int period = 2 * (len - 1);
+    p %= period;
+    if (p >= len) p = period - p;
+    return p;
+}
+
+KO_API int ko_pyrdown_f32(const float* src, size_t sw, size_t sh, size_t C, float* dst) {
+    const size_t dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+    static const float k1[5] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+    float kw[25];
+    for (int y = 0, i = 0; y < 5; ++y) for (int x = 0; x < 5; ++x) kw[i++] = k1[y] * k1[x];
+    // reflect_101 is the identity on interior coordinates, so the reference's centre / border split is one loop here
+    for (size_t dy = 0; dy < dh; ++dy)
+        for (size_t dx = 0; dx < dw; ++dx)
+            for (size_t c = 0; c < C; ++c) {
+                float sum = 0.0f;
+                int k = 0;
+                for (int ky = 0; ky < 5; ++ky) {
+                    const size_t sy = (size_t)reflect_101((int)(dy * 2) + ky - 2, (int)sh);
+                    for (int kx = 0; kx < 5; ++kx) {
+                        const size_t sx = (size_t)reflect_101((int)(dx * 2) + kx - 2, (int)sw);
+                        sum += src[(sy * sw + sx) * C + c] * kw[k++];
+                    }
+                }
+                dst[(dy * dw + dx) * C + c] = sum;
+            }
+    return 0;
+}
+
+KO_API int ko_pyrup_f32(const float* src, size_t sw, size_t sh, size_t C, float* dst) {
+    const float SCALE_EVEN = 0.125f, SCALE_ODD = 0.5f, W_CENTER = 6.0f, W_NEIGHBOR = 1.0f, W_BORDER = 7.0f;
+    const size_t dw = sw * 2, stride = dw * C;
+    std::vector<float> buf(dw * sh * C);
+    for (size_t y = 0; y < sh; ++y) {  // horizontal pass, pyramid.rs:22-90
+        const float* s = src + y * sw * C;
+        float* d = buf.data() + y * stride;
+        if (sw == 1) {
+            for (size_t k = 0; k < C; ++k) { d[k] = s[k]; if (k + C < stride) d[k + C] = s[k]; }
+            continue;
+        }
+        for (size_t k = 0; k < C; ++k) {
+            const float l = s[k], r = s[C + k];
+            d[k] = (W_CENTER * l + 2.0f * r) * SCALE_EVEN;
+            d[C + k] = (l + r) * SCALE_ODD;
+        }
+        for (size_t x = 1; x + 1 < sw; ++x)
+            for (size_t k = 0; k < C; ++k) {
+                const float p = s[(x - 1) * C + k], c = s[x * C + k], n = s[(x + 1) * C + k];
+                d[2 * x * C + k] = (W_NEIGHBOR * p + W_CENTER * c + W_NEIGHBOR * n) * SCALE_EVEN;
+                d[2 * x * C + C + k] = (c + n) * SCALE_ODD;
+            }
+        const size_t lx = sw - 1;
+        for (size_t k = 0; k < C; ++k) {
+            const float p = s[(lx - 1) * C + k], c = s[lx * C + k];
+            d[2 * lx * C + k] = (W_NEIGHBOR * p + W_BORDER * c) * SCALE_EVEN;
+            d[2 * lx * C + C + k] = c;
+        }
+    }
+    for (size_t y = 0; y < sh; ++y) {  // vertical pass, pyramid.rs:98-160
+        size_t rt, rc, rb;
+        if (sh == 1) { rt = rc = rb = 0; }
+        else if (y == 0) { rt = 0; rc = 0; rb = 1; }
+        else if (y == sh - 1) { rt = sh - 2; rc = sh - 1; rb = sh - 1; }
+        else { rt = y - 1; rc = y; rb = y + 1; }
+        const float *t = buf.data() + rt * stride, *c = buf.data() + rc * stride, *b = buf.data() + rb * stride;
+        float* even = dst + (2 * y) * stride;
+        float* odd = even + stride;
+        for (size_t i = 0; i < stride; ++i) {
+            if (y == 0) {
+                even[i] = (W_CENTER * c[i] + 2.0f * b[i]) * SCALE_EVEN;
+                odd[i] = (c[i] + b[i]) * SCALE_ODD;
+            } else if (y == sh - 1) {
+                even[i] = (W_NEIGHBOR * t[i] + W_BORDER * c[i]) * SCALE_EVEN;
+                odd[i] = c[i];
+            } else {
+                even[i] = (W_NEIGHBOR * t[i] + W_CENTER * c[i] + W_NEIGHBOR * b[i]) * SCALE_EVEN;
+                odd[i] = (c[i] + b[i]) * SCALE_ODD;
+            }
+        }
+    }
+    return 0;
+}
+
+KO_API int ko_pyrdown_u8(const uint8_t* src, size_t sw, size_t sh, size_t C, uint8_t* dst) {
+    const size_t dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+    std::vector<uint16_t> buf(dw * sh * C);
+    for (size_t y = 0; y < sh; ++y)
+        for (size_t dx = 0; dx < dw; ++dx) {
+            size_t ix[5];
+            for (int t = 0; t < 5; ++t) ix[t] = (size_t)reflect_101((int)(dx * 2) + t - 2, (int)sw) * C;
+            for (size_t k = 0; k < C; ++k) {
+                const uint8_t* r = src + y * sw * C + k;
+                buf[(y * dw + dx) * C + k] = (uint16_t)(r[ix[0]] + 4 * r[ix[1]] + 6 * r[ix[2]] + 4 * r[ix[3]] + r[ix[4]]);
+            }
+        }
+    const size_t stride = dw * C;
+    for (size_t dy = 0; dy < dh; ++dy) {
+        size_t off[5];
+        for (int t = 0; t < 5; ++t) off[t] = (size_t)reflect_101((int)(dy * 2) + t - 2, (int)sh) * stride;
+        for (size_t i = 0; i < stride; ++i) {
+            const uint32_t sum = (uint32_t)buf[off[0] + i] + 4u * buf[off[1] + i] + 6u * buf[off[2] + i] + 4u * buf[off[3] + i] + buf[off[4] + i];
+            dst[dy * stride + i] = (uint8_t)std::min<uint32_t>((sum + 128u) >> 8, 255u);
+        }
+    }
+    return 0;
+}
+
+KO_API int ko_pyrup_u8(const uint8_t* src, size_t sw, size_t sh, size_t C, uint8_t* dst) {
+    const size_t dw = sw * 2, stride = dw * C;
+    std::vector<uint8_t> buf(dw * sh * C);
+    for (size_t y = 0; y < sh; ++y)
+        for (size_t x = 0; x < sw; ++x) {
+            const size_t ip = (size_t)reflect_101((int)x - 1, (int)sw) * C, in = (size_t)reflect_101((int)x + 1, (int)sw) * C;
+            for (size_t k = 0; k < C; ++k) {
+                const uint8_t* r = src + y * sw * C + k;
+                const uint16_t c = r[x * C], p = r[ip], n = r[in];
+                buf[y * stride + 2 * x * C + k] = (uint8_t)((p + 6 * c + n + 4) >> 3);
+                if ((2 * x + 1) * C < stride) buf[y * stride + (2 * x + 1) * C + k] = (uint8_t)((c + n + 1) >> 1);
+            }
+        }
+    for (size_t y = 0; y < sh; ++y) {
+        const uint8_t* p = buf.data() + (size_t)reflect_101((int)y - 1, (int)sh) * stride;
+        const uint8_t* c = buf.data() + y * stride;
+        const uint8_t* n = buf.data() + (size_t)reflect_101((int)y + 1, (int)sh) * stride;
+        uint8_t* even = dst + 2 * y * stride;
+        uint8_t* odd = even + stride;
+        for (size_t i = 0; i < stride; ++i) {
+            even[i] = (uint8_t)(((uint16_t)p[i] + 6 * (uint16_t)c[i] + n[i] + 4) >> 3);
+            odd[i] = (uint8_t)(((uint16_t)c[i] + n[i] + 1) >> 1);
+        }
+    }
+    return 0;
+}

@@ -563,3 +563,21 @@ def lanczos_axis(src_len: int, dst_len: int):
     x0s, w = np.empty(dst_len, np.int32), np.empty(dst_len * 6, np.float32)
     lib().ko_lanczos_axis(src_len, dst_len, _p(x0s), _p(w))
     return x0s, w.reshape(dst_len, 6)
+
+
+# ── pyramids ───────────────────────────────────────────────
+def _pyr(fn: str, src: np.ndarray, up: bool, dtype):
+    src = np.ascontiguousarray(src, dtype)
+    sh, sw, c = src.shape
+    dst = np.empty((sh * 2, sw * 2, c) if up else ((sh + 1) // 2, (sw + 1) // 2, c), dtype)
+    f = getattr(lib(), fn)
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p]
+    f.restype = C.c_int
+    assert f(_p(src), sw, sh, c, _p(dst)) == 0
+    return dst
+
+
+def pyrdown_f32(src): return _pyr("ko_pyrdown_f32", src, False, np.float32)
+def pyrup_f32(src): return _pyr("ko_pyrup_f32", src, True, np.float32)
+def pyrdown_u8(src): return _pyr("ko_pyrdown_u8", src, False, np.uint8)
+def pyrup_u8(src): return _pyr("ko_pyrup_u8", src, True, np.uint8)

@@ -473,3 +473,31 @@ def test_preprocess_lanczos_vs_oracle(kb, oracle, dev, fmt, bpp, f16):
     got = dst.float().cpu().numpy()
     tol = 2e-3 if f16 else 1e-4
     assert np.max(np.abs(got - want)) <= tol, np.max(np.abs(got - want))
+
+
+# ── pyramids ───────────────────────────────────────────────────
+@pytest.mark.parametrize("w,h,c,n", [(53, 37, 3, 2), (16, 16, 1, 1), (7, 5, 4, 3), (2, 2, 3, 1), (1, 1, 1, 1), (1, 6, 3, 1), (9, 1, 1, 2), (640, 360, 3, 2)])
+def test_pyramids(kb, oracle, dev, w, h, c, n):
+    f = oracle.pattern_f32(n * w * h * c, 8).reshape(n, h, w, c)
+    u = oracle.pattern_u8(n * w * h * c, 9).reshape(n, h, w, c)
+    for data, dt, down, up in ((f, torch.float32, oracle.pyrdown_f32, oracle.pyrup_f32), (u, torch.uint8, oracle.pyrdown_u8, oracle.pyrup_u8)):
+        src = kb.Image(cu(data, dev))
+        dn = kb.Image.zeros_cuda(kb.ImageSize((w + 1) // 2, (h + 1) // 2), c, dt, dev, batch=n)
+        kb.imgproc.pyrdown(src, dn)
+        want = np.stack([down(data[i]) for i in range(n)])
+        (assert_f32_equal if dt == torch.float32 else np.testing.assert_array_equal)(dn.numpy().reshape(want.shape), want)
+        upi = kb.Image.zeros_cuda(kb.ImageSize(2 * w, 2 * h), c, dt, dev, batch=n)
+        kb.imgproc.pyrup(src, upi)
+        want = np.stack([up(data[i]) for i in range(n)])
+        (assert_f32_equal if dt == torch.float32 else np.testing.assert_array_equal)(upi.numpy().reshape(want.shape), want)
+    with pytest.raises(kb.ImageError, match="Invalid image size"):
+        kb.imgproc.pyrdown(kb.Image(cu(f, dev)), kb.Image.zeros_cuda(kb.ImageSize(w + 3, h), c, torch.float32, dev, batch=n))
+
+
+def test_build_pyramid_levels(kb, oracle, dev):
+    """pyramid.rs:851-883 `test_build_pyramid_levels_and_sizes_odd_dimensions`: 5x7 -> 3x4 -> 2x2 -> 1x1."""
+    src = kb.Image(cu(np.ones((7, 5, 1), np.float32), dev))
+    pyr = kb.imgproc.build_pyramid(src, 3)
+    assert [(p.cols(), p.rows()) for p in pyr] == [(5, 7), (3, 4), (2, 2), (1, 1)]
+    for p in pyr:
+        assert np.all(p.numpy() == np.float32(1.0))

@@ -879,3 +879,40 @@ def test_preprocess_lanczos_solid_and_bounds(oracle):
     inside = out[:, 3:17, :]
     assert np.max(np.abs(inside - np.float32(200.0) / np.float32(255.0))) < 1e-5
     assert np.all(out[:, 0, :] == np.float32(114.0) / np.float32(255.0))
+
+
+# ── pyramids ────────────────────────────────────────────────
+def test_pyrdown_reference_vectors(oracle):
+    """pyramid.rs:915-994 `test_pyrdown`, `test_pyrdown_3c` expected arrays; :1372-1418 `test_pyrdown_u8_3c` (cv2.pyrDown)."""
+    got = oracle.pyrdown_f32(np.arange(16, dtype=np.float32).reshape(4, 4, 1)).reshape(-1)
+    assert np.max(np.abs(got - np.array([3.75, 4.875, 8.25, 9.375], np.float32))) < 1e-4
+    got = oracle.pyrdown_f32(np.arange(48, dtype=np.float32).reshape(4, 4, 3)).reshape(-1)
+    want = [11.25, 12.25, 13.25, 14.625, 15.625, 16.625, 24.75, 25.75, 26.75, 28.125, 29.125, 30.125]
+    assert np.max(np.abs(got - np.array(want, np.float32))) < 1e-4
+    got8 = oracle.pyrdown_u8(np.arange(48, dtype=np.uint8).reshape(4, 4, 3)).reshape(-1)
+    assert np.array_equal(got8, [11, 12, 13, 15, 16, 17, 25, 26, 27, 28, 29, 30])
+
+
+def test_pyramids_against_cv2(oracle):
+    """The reference documents cv2 as the cross-check of its pyramid levels (pyramid.rs:1373-1376).  pyrdown: byte-exact
+    (u8) / 1e-6 (f32) everywhere; pyrup: the interior (the reference's border rule is its own)."""
+    cv2 = pytest.importorskip("cv2")
+    for (h, w, c) in ((37, 53, 3), (16, 16, 1), (5, 7, 4), (2, 2, 3)):
+        a = oracle.pattern_u8(h * w * c, 5).reshape(h, w, c)
+        f = oracle.pattern_f32(h * w * c, 6).reshape(h, w, c)
+        assert np.array_equal(oracle.pyrdown_u8(a), cv2.pyrDown(a).reshape((h + 1) // 2, (w + 1) // 2, c))
+        assert np.max(np.abs(oracle.pyrdown_f32(f) - cv2.pyrDown(f).reshape((h + 1) // 2, (w + 1) // 2, c))) < 1e-6
+        if h > 4 and w > 4:
+            up8 = oracle.pyrup_u8(a).astype(int)[2:-2, 2:-2]
+            assert np.max(np.abs(up8 - cv2.pyrUp(a).reshape(2 * h, 2 * w, c).astype(int)[2:-2, 2:-2])) <= 1
+            upf = oracle.pyrup_f32(f)[2:-2, 2:-2]
+            assert np.max(np.abs(upf - cv2.pyrUp(f).reshape(2 * h, 2 * w, c)[2:-2, 2:-2])) < 1e-6
+
+
+def test_pyramid_min_sizes_and_flat(oracle):
+    """pyramid.rs:1050-1111 / :1218-1244 / :1246-1278: 1x1, 1xN, Nx1 inputs work; a flat image stays flat."""
+    for (h, w) in ((1, 1), (1, 5), (5, 1), (2, 3)):
+        f = np.full((h, w, 1), 0.625, np.float32)
+        assert np.all(oracle.pyrdown_f32(f) == np.float32(0.625)) and np.all(oracle.pyrup_f32(f) == np.float32(0.625))
+        u = np.full((h, w, 3), 77, np.uint8)
+        assert np.all(oracle.pyrdown_u8(u) == 77) and np.all(oracle.pyrup_u8(u) == 77)
