@@ -684,3 +684,21 @@ def build_pyramid(src: Image, max_level: int) -> list[Image]:
         pyrdown(cur, nxt)
         levels.append(nxt)
     return levels
+
+
+# ── calibration: undistort maps (calibration/distortion.rs) ──────────────────
+def generate_correction_map_polynomial(intrinsic: Sequence[float], distortion: Sequence[float], size: ImageSize, device) -> tuple[Image, Image]:
+    """calibration/distortion.rs:135 — (map_x, map_y), each an H x W x 1 f32 device Image, for `remap`: the distorted source
+    coordinate of every destination pixel under the polynomial (Brown-Conrady rational) model.  `intrinsic` = (fx, fy, cx,
+    cy) of CameraIntrinsic, `distortion` = (k1, k2, k3, k4, k5, k6, p1, p2) of PolynomialDistortion.  Generated on the
+    device — the reference builds the maps on the host and uploads them."""
+    if len(intrinsic) != 4 or len(distortion) != 8:
+        raise ValueError("intrinsic = (fx, fy, cx, cy), distortion = (k1..k6, p1, p2)")
+    dev = torch.device(device)
+    _lib.set_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    mx = Image.zeros_cuda(size, 1, torch.float32, dev)
+    my = Image.zeros_cuda(size, 1, torch.float32, dev)
+    _check(_lib.lib().kb200_generate_correction_map_polynomial(_stream(dev), (C.c_double * 4)(*[float(v) for v in intrinsic]),
+                                                              (C.c_double * 8)(*[float(v) for v in distortion]), size.width, size.height,
+                                                              mx.data.data_ptr(), my.data.data_ptr(), mx.numel()))
+    return mx, my

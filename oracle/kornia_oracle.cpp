@@ -1733,3 +1733,35 @@ KO_API int ko_pyrup_u8(const uint8_t* src, size_t sw, size_t sh, size_t C, uint8
     }
     return 0;
 }
+
+// ─────────────────────────────────────────────────────────────────────────────
+// §8(f) #2: undistort maps — calibration/distortion.rs:60-103 (distort_point_polynomial, f64, unfused),
+// :135-150 (generate_correction_map_polynomial: per destination pixel, cast to f32).
+// intr = {fx, fy, cx, cy}; dist = {k1..k6, p1, p2}.
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API void ko_distort_point_polynomial(double x, double y, const double intr[4], const double dist[8], double out[2]) {
+    const double fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3];
+    const double k1 = dist[0], k2 = dist[1], k3 = dist[2], k4 = dist[3], k5 = dist[4], k6 = dist[5], p1 = dist[6], p2 = dist[7];
+    x = (x - cx) / fx;
+    y = (y - cy) / fy;
+    const double r2 = x * x + y * y;
+    const double r4 = r2 * r2;
+    const double r6 = r4 * r2;
+    const double kr = (1.0 + k1 * r2 + k2 * r4 + k3 * r6) / (1.0 + k4 * r2 + k5 * r4 + k6 * r6);
+    const double x_2 = 2.0 * x, y_2 = 2.0 * y;
+    const double xy_2 = x_2 * y;
+    const double xd = x * kr + xy_2 * p1 + p2 * (r2 + x_2 * x);
+    const double yd = y * kr + p1 * (r2 + y_2 * y) + xy_2 * p2;
+    out[0] = fx * xd + cx;
+    out[1] = fy * yd + cy;
+}
+
+KO_API void ko_generate_correction_map_polynomial(const double intr[4], const double dist[8], size_t w, size_t h, float* map_x, float* map_y) {
+    for (size_t y = 0; y < h; ++y)
+        for (size_t x = 0; x < w; ++x) {
+            double o[2];
+            ko_distort_point_polynomial((double)x, (double)y, intr, dist, o);
+            map_x[y * w + x] = (float)o[0];
+            map_y[y * w + x] = (float)o[1];
+        }
+}

@@ -581,3 +581,21 @@ def pyrdown_f32(src): return _pyr("ko_pyrdown_f32", src, False, np.float32)
 def pyrup_f32(src): return _pyr("ko_pyrup_f32", src, True, np.float32)
 def pyrdown_u8(src): return _pyr("ko_pyrdown_u8", src, False, np.uint8)
 def pyrup_u8(src): return _pyr("ko_pyrup_u8", src, True, np.uint8)
+
+
+# ── undistort maps ─────────────────────────────────────────
+def distort_point_polynomial(x: float, y: float, intrinsic, distortion):
+    intr, dist, out = np.array(intrinsic, np.float64), np.array(distortion, np.float64), np.empty(2, np.float64)
+    f = lib().ko_distort_point_polynomial
+    f.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]; f.restype = None
+    f(float(x), float(y), _p(intr), _p(dist), _p(out))
+    return float(out[0]), float(out[1])
+
+
+def generate_correction_map_polynomial(intrinsic, distortion, w: int, h: int):
+    intr, dist = np.array(intrinsic, np.float64), np.array(distortion, np.float64)
+    mx, my = np.empty((h, w, 1), np.float32), np.empty((h, w, 1), np.float32)
+    f = lib().ko_generate_correction_map_polynomial
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]; f.restype = None
+    f(_p(intr), _p(dist), w, h, _p(mx), _p(my))
+    return mx, my

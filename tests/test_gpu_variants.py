@@ -501,3 +501,28 @@ def test_build_pyramid_levels(kb, oracle, dev):
     assert [(p.cols(), p.rows()) for p in pyr] == [(5, 7), (3, 4), (2, 2), (1, 1)]
     for p in pyr:
         assert np.all(p.numpy() == np.float32(1.0))
+
+
+# ── undistort maps on the device ───────────────────────────────
+DIST_INTR = (577.48583984375, 652.8748779296875, 577.48583984375, 386.1428833007813)
+DIST_COEF = (1.7547749280929563, 0.0097926277667284, -0.027250492945313457, 2.1092164516448975, 0.462927520275116, -0.08215277642011642,
+             -0.00005457743463921361, 0.00003006766564794816)
+
+
+@pytest.mark.parametrize("w,h", [(8, 4), (641, 479), (1920, 1080)])
+def test_generate_correction_map_polynomial(kb, oracle, dev, w, h):
+    mx, my = kb.imgproc.generate_correction_map_polynomial(DIST_INTR, DIST_COEF, kb.ImageSize(w, h), dev)
+    ox, oy = oracle.generate_correction_map_polynomial(DIST_INTR, DIST_COEF, w, h)
+    assert_f32_equal(mx.numpy(), ox, "map_x"); assert_f32_equal(my.numpy(), oy, "map_y")
+
+
+def test_undistort_pipeline_map_then_remap(kb, oracle, dev):
+    """The undistort caller of config 5: maps generated on the device feed remap on the same stream, f32 and u8."""
+    w, h = 640, 480
+    intr, coef = (612.3, 610.8, 320.1, 241.7), (-0.12, 0.03, 0.0, 0.0, 0.0, 0.0, 1e-4, -2e-4)
+    mx, my = kb.imgproc.generate_correction_map_polynomial(intr, coef, kb.ImageSize(w, h), dev)
+    ox, oy = oracle.generate_correction_map_polynomial(intr, coef, w, h)
+    src = oracle.pattern_f32(w * h * 3).reshape(h, w, 3)
+    dst = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev)
+    kb.imgproc.remap(kb.Image(cu(src, dev)), dst, mx, my, kb.InterpolationMode.Bilinear)
+    assert_f32_equal(dst.numpy(), oracle.remap(src, ox, oy, oracle.BILINEAR), "undistort f32")

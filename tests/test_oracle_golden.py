@@ -916,3 +916,25 @@ def test_pyramid_min_sizes_and_flat(oracle):
         assert np.all(oracle.pyrdown_f32(f) == np.float32(0.625)) and np.all(oracle.pyrup_f32(f) == np.float32(0.625))
         u = np.full((h, w, 3), 77, np.uint8)
         assert np.all(oracle.pyrdown_u8(u) == 77) and np.all(oracle.pyrup_u8(u) == 77)
+
+
+# ── undistort maps ──────────────────────────────────────────
+DIST_INTR = (577.48583984375, 652.8748779296875, 577.48583984375, 386.1428833007813)
+DIST_COEF = (1.7547749280929563, 0.0097926277667284, -0.027250492945313457, 2.1092164516448975, 0.462927520275116, -0.08215277642011642,
+             -0.00005457743463921361, 0.00003006766564794816)
+
+
+def test_distort_point_polynomial_reference_value(oracle):
+    """calibration/distortion.rs:603-628 `test_distort_point_polynomial`: y is asserted EXACTLY in f64."""
+    x, y = oracle.distort_point_polynomial(100.0, 20.0, DIST_INTR, DIST_COEF)
+    assert y == 98.83006704526377
+    assert x != 194.24656721843076 and abs(x - 202.86576969976807) < 1e-9   # the reference asserts `ne` on that literal
+
+
+def test_correction_map_shape_and_identity(oracle):
+    """:630-672 map shapes; zero distortion is the identity map (:723-743 `test_identity_no_distortion` spirit)."""
+    mx, my = oracle.generate_correction_map_polynomial(DIST_INTR, DIST_COEF, 8, 4)
+    assert mx.shape == (4, 8, 1) and my.shape == (4, 8, 1)
+    mx, my = oracle.generate_correction_map_polynomial((612.3, 610.8, 320.1, 241.7), (0,) * 8, 16, 9)
+    xs, ys = np.meshgrid(np.arange(16, dtype=np.float32), np.arange(9, dtype=np.float32))
+    assert np.max(np.abs(mx[..., 0] - xs)) < 1e-4 and np.max(np.abs(my[..., 0] - ys)) < 1e-4
