@@ -102,7 +102,7 @@ def test_argument_validation_without_a_gpu(kb):
     assert l.kb200_warp_perspective_f32_c3(None, p, 64, p, 64, 2, 2, 2, 2, 1, _lib.f3([1, 2, 3, 2, 4, 6, 3, 6, 9], 9), 1) \
         == _lib.ERR_SINGULAR_MATRIX
     assert err() == "homography matrix is singular (|det| < 1e-10)"  # cuda/warp_perspective.rs:408-410
-    assert l.kb200_warp_affine_f32_c3(None, p, 64, p, 64, 2, 2, 2, 2, 1, _lib.f3([1, 0, 0, 0, 1, 0], 6), 2) == _lib.ERR_UNSUPPORTED
+    assert l.kb200_warp_affine_f32_c3(None, p, 64, p, 64, 2, 2, 2, 2, 1, _lib.f3([1, 0, 0, 0, 1, 0], 6), 7) == _lib.ERR_UNSUPPORTED   # 0..3 = Nearest/Bilinear/Bicubic/Lanczos
     assert l.kb200_sobel_f32(None, p, 64, p, 64, 2, 2, 3, 1, 7) == _lib.ERR_INVALID_KERNEL
     assert l.kb200_separable_filter_f32(None, p, 64, p, 64, None, _lib.f3([1] * 3), 0, _lib.f3([1] * 3), 3, 2, 2, 3, 1) == _lib.ERR_INVALID_KERNEL
     assert l.kb200_resize_bilinear_u8(None, p, 64, p, 64, 1, 4, 2, 2, 3, 1) == _lib.ERR_INVALID_ARGUMENT  # needs >= 2x2
@@ -117,7 +117,7 @@ def test_argument_validation_without_a_gpu(kb):
     assert l.kb200_preprocess_src_bytes(C.byref(d)) == 72
     assert l.kb200_preprocess_f32(None, C.byref(d), ptrs, lens, 1, p, 64) == _lib.ERR_INVALID_SOURCE
     assert "got 60 bytes, need 72" in err()  # preprocess.rs:1287-1300
-    d.sampling = 3
+    d.sampling = 2   # Bicubic: UnsupportedSampling in the reference too (preprocess.rs:1044-1051); 3 = Lanczos is supported
     assert l.kb200_preprocess_f32(None, C.byref(d), ptrs, lens, 1, p, 64) == _lib.ERR_UNSUPPORTED
     assert l.kb200_status_name(_lib.ERR_SLICE_TOO_SMALL) == b"KB200_ERR_SLICE_TOO_SMALL"
 
