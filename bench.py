@@ -509,6 +509,50 @@ def op_table(kb, dev, peak_gbs: float, quick: bool, n_gpus: int, rank: int) -> d
     return out
 
 
+def e2e_config3(kb, dev, st, n: int, steps: int, n_gpus: int) -> dict:
+    import torch
+
+    w, h = 1920, 1080
+    frame = w * h * 3 // 2
+    base = ((torch.arange(frame, dtype=torch.int64) * 7 + 13) % 251)
+    host = torch.empty((n, frame), dtype=torch.uint8, pin_memory=True)
+    for k in range(n):
+        host[k] = ((base + 31 * (kb.dist.rank() * n + k)) & 0xFF).to(torch.uint8)
+    pre = kb.Preprocessor.builder().source_format(kb.SourceFormat.Nv12).mode(kb.ResizeMode.Stretch).normalize(kb.Normalize.imagenet()).build_cuda()
+    chunk = 8
+    out = {}
+    for tag, f16 in (("f32", False), ("f16", True)):
+        esz = 2 if f16 else 4
+        pipe = kb.imgproc.HostPipeline(dev, src_chunk_bytes=chunk * (frame + 16), dst_chunk_bytes=chunk * 3 * w * h * esz, depth=3)
+        dst = torch.empty((n, 3, h, w), dtype=torch.float16 if f16 else torch.float32, pin_memory=True)
+        fn = lambda: pre.run_raw_host(host, w, h, (w, h), out=dst, f16=f16, pipeline=pipe)
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        kb.dist.barrier(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(steps):
+            fn()
+        e1.record(st)
+        torch.cuda.synchronize()
+        kb.dist.barrier(dev)
+        ms = kb.dist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+        h2d, d2h = pipe.last_transfer()
+        # spot check against the device-buffer path
+        dev_dst = torch.empty((2, 3, h, w), dtype=dst.dtype, device=dev)
+        (pre.run_raw_batch_f16 if f16 else pre.run_raw_batch)([host[i].to(dev) for i in range(2)], w, h, dev_dst)
+        same = bool(torch.equal(dev_dst.cpu(), dst[:2]))
+        pipe.close()
+        out[tag] = {"value": n_gpus * n * w * h / 1e6 / (ms * 1e-3), "unit": "Mpix/s", "ms_per_step": ms, "frames_per_gpu": n, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "h2d_gbs_per_rank": round(h2d / ms / 1e6, 1), "d2h_gbs_per_rank": round(d2h / ms / 1e6, 1),
+                    "matches_device_result": same}
+        del dst, dev_dst
+    out["how"] = ("Preprocessor.run_raw_host (kb200_preprocess_host): NV12 1080p frames from pinned host memory -> [N,3,1080,1920] host tensor; "
+                  f"chunks of {chunk} frames over a 3-stream ring, one fused launch per chunk")
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -636,6 +680,10 @@ def main() -> None:
                "host_src_bytes_per_step": BATCH * SW * SH * 3, "row_map": list(row_map),
                "how": f"kb200_resize_normalize_chw_u8_f32_host on pinned host buffers: chunks of <= {chunk} frames over a {nstreams}-stream ring "
                       f"(strided upload of the tapped source rows only — period/first/keep = {row_map} — kernel, download)"}
+        # config 3 end to end: raw NV12 camera frames in HOST memory -> normalised CHW tensor in HOST memory through
+        # Preprocessor.run_raw_host (kb200_preprocess_host): f32, and the reference's f16 output (preprocess.rs:1086) which
+        # halves the download — the larger half of the link traffic
+        e2e["config3"] = e2e_config3(kb, dev, st, 16 if args.quick else 64, max(2, min(args.steps, 6)), n_gpus)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     del src, dst
 

@@ -102,6 +102,7 @@ def _declare(l: C.CDLL) -> None:
         "kb200_preprocess_f32": ([vp, C.POINTER(PreprocessDesc), C.POINTER(vp), C.POINTER(sz), u32, vp, sz], i),
         "kb200_preprocess_f16": ([vp, C.POINTER(PreprocessDesc), C.POINTER(vp), C.POINTER(sz), u32, vp, sz], i),
         "kb200_preprocess_strided_f32": ([vp, C.POINTER(PreprocessDesc), vp, sz, sz, u32, vp, sz], i),
+        "kb200_preprocess_host": ([vp, vp, C.POINTER(PreprocessDesc), vp, sz, sz, u32, vp, sz, i], i),
         "kb200_preprocess_strided_f16": ([vp, C.POINTER(PreprocessDesc), vp, sz, sz, u32, vp, sz], i),
     }
     for name, (args, res) in sig.items():

@@ -32,6 +32,12 @@ struct kb200_host_pipeline {
 
 using namespace kb200;
 
+namespace kb200 {   // preprocess.cu
+int preprocess_validate(const kb200_preprocess_desc* desc);
+size_t preprocess_frame_bytes(const kb200_preprocess_desc& d);
+int preprocess_launch_strided(cudaStream_t s, const kb200_preprocess_desc& d, const uint8_t* base, size_t stride, uint32_t batch, void* dst, bool f16);
+}
+
 namespace {
 
 int cuda_fail(const char* what, cudaError_t e) { return fail(KB200_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e)); }
@@ -154,6 +160,60 @@ KB200_API int kb200_resize_normalize_chw_u8_f32_host(kb200_host_pipeline* pipe, 
         KB200_TRY(launch_fused_resize(s, pipe->src[k], reinterpret_cast<float*>(pipe->dst[k]), p, n));
         KB200_CUDA(cudaMemcpyAsync(host_dst + (size_t)f0 * dw * dh * 3, pipe->dst[k], dst_frame * n, cudaMemcpyDeviceToHost, s));
         pipe->h2d_bytes += src_frame_dev * n;
+        pipe->d2h_bytes += dst_frame * n;
+        f0 += n;
+    }
+    for (int k = 0; k < used; ++k) {
+        KB200_CUDA(cudaEventRecord(pipe->done[k], pipe->streams[k]));
+        KB200_CUDA(cudaStreamWaitEvent(user, pipe->done[k], 0));
+    }
+    return KB200_OK;
+}
+
+
+// Host-buffer form of Preprocessor::run_raw_batch (preprocess.rs:1234; the reference's Python Preprocessor pins and
+// uploads camera frames itself, kornia-py/src/cuda_ext/mod.rs:700-760): `batch` raw frames at host_base + i*frame_stride
+// (page-locked memory for overlap) -> host tensor [batch,3,dst_h,dst_w] f32 or binary16.  Chunks of frames ride the same
+// stream ring as the fused resize: upload -> fused preprocess kernel (one launch per chunk) -> download.
+KB200_API int kb200_preprocess_host(kb200_host_pipeline* pipe, kb200_stream_t stream, const kb200_preprocess_desc* desc,
+                                    const uint8_t* host_base, size_t base_len, size_t frame_stride, uint32_t batch, void* host_dst,
+                                    size_t dst_len, int out_f16) {
+    KB200_TRY(check_ptr("pipeline", pipe));
+    KB200_TRY(preprocess_validate(desc));
+    KB200_TRY(check_ptr("base", host_base)); KB200_TRY(check_ptr("dst", host_dst));
+    if (batch == 0) return fail(KB200_ERR_INVALID_ARGUMENT, "batch must be non-zero");
+    const size_t need = preprocess_frame_bytes(*desc);
+    if (frame_stride < need && batch > 1) return fail(KB200_ERR_INVALID_SOURCE, "frame stride %zu smaller than a frame (%zu bytes)", frame_stride, need);
+    if (base_len < (size_t)(batch - 1) * frame_stride + need)
+        return fail(KB200_ERR_INVALID_SOURCE, "invalid raw source at %dx%d (got %zu bytes, need %zu)", desc->src_w, desc->src_h, base_len,
+                    (size_t)(batch - 1) * frame_stride + need);
+    const size_t dst_frame_elems = (size_t)3 * desc->dst_w * desc->dst_h;
+    KB200_TRY(check_slice("dst", dst_len, dst_frame_elems * batch));
+    pipe->h2d_bytes = pipe->d2h_bytes = 0;
+    KB200_CUDA(cudaSetDevice(pipe->device));
+    const size_t elem = out_f16 ? 2 : 4;
+    const size_t dst_frame = dst_frame_elems * elem;
+    const size_t dev_stride = (need + 15) & ~(size_t)15;      // staged frames 16-byte aligned (the NV12 fast paths want aligned bases)
+    const size_t per_chunk = std::min<size_t>(std::min(pipe->src_bytes / dev_stride, pipe->dst_bytes / dst_frame), 256);
+    if (per_chunk == 0)
+        return fail(KB200_ERR_INVALID_ARGUMENT, "pipeline staging (%zu B src, %zu B dst) is smaller than one frame (%zu B, %zu B)", pipe->src_bytes,
+                    pipe->dst_bytes, dev_stride, dst_frame);
+    cudaStream_t user = as_stream(stream);
+    KB200_CUDA(cudaEventRecord(pipe->start, user));
+    for (int k = 0; k < pipe->depth; ++k) KB200_CUDA(cudaStreamWaitEvent(pipe->streams[k], pipe->start, 0));
+    uint32_t f0 = 0;
+    int used = 0;
+    for (uint32_t ci = 0; f0 < batch; ++ci) {
+        const int k = (int)(ci % (uint32_t)pipe->depth);
+        used = std::max(used, k + 1);
+        const uint32_t n = (uint32_t)std::min<size_t>(per_chunk, batch - f0);
+        cudaStream_t s = pipe->streams[k];
+        const uint8_t* hs = host_base + (size_t)f0 * frame_stride;
+        if (frame_stride == need && dev_stride == need) KB200_CUDA(cudaMemcpyAsync(pipe->src[k], hs, need * n, cudaMemcpyHostToDevice, s));
+        else KB200_CUDA(cudaMemcpy2DAsync(pipe->src[k], dev_stride, hs, frame_stride, need, n, cudaMemcpyHostToDevice, s));
+        KB200_TRY(preprocess_launch_strided(s, *desc, pipe->src[k], dev_stride, n, pipe->dst[k], out_f16 != 0));
+        KB200_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(host_dst) + (size_t)f0 * dst_frame, pipe->dst[k], dst_frame * n, cudaMemcpyDeviceToHost, s));
+        pipe->h2d_bytes += need * n;
         pipe->d2h_bytes += dst_frame * n;
         f0 += n;
     }

@@ -456,6 +456,13 @@ static int launch_preprocess(cudaStream_t s, const kb200_preprocess_desc& d, con
     return KB200_OK;
 }
 
+// used by the host-buffer pipeline (host_pipeline.cu): frames already staged at base + i*stride on the device
+int preprocess_validate(const kb200_preprocess_desc* desc) { return validate_desc(desc); }
+size_t preprocess_frame_bytes(const kb200_preprocess_desc& d) { return src_bytes(d); }
+int preprocess_launch_strided(cudaStream_t s, const kb200_preprocess_desc& d, const uint8_t* base, size_t stride, uint32_t batch, void* dst, bool f16) {
+    return f16 ? launch_preprocess<true>(s, d, nullptr, base, stride, batch, dst) : launch_preprocess<false>(s, d, nullptr, base, stride, batch, dst);
+}
+
 template <bool F16>
 static int preprocess_entry(kb200_stream_t stream, const kb200_preprocess_desc* desc, const uint8_t* const* frames,
                             const size_t* frame_len, const uint8_t* base, size_t base_len, size_t stride,

@@ -327,6 +327,39 @@ class Preprocessor:
     def run_raw_batch_f16(self, frames: Sequence[torch.Tensor], src_w: int, src_h: int, dst: torch.Tensor) -> None:
         self._run_raw_batch(frames, src_w, src_h, dst, True, False)
 
+    def run_raw_host(self, host_frames: torch.Tensor, src_w: int, src_h: int, dst_size: tuple[int, int], out: torch.Tensor | None = None,
+                     f16: bool = False, pipeline=None) -> torch.Tensor:
+        """HOST camera frames in, HOST tensor out — what the reference's Python `Preprocessor` does around its kernel (pinned
+        staging, upload, launch: kornia-py/src/cuda_ext/mod.rs:700-760), as one call: `host_frames` is a [N, frame_bytes] uint8
+        host tensor (page-locked for overlap), the result a [N,3,H,W] f32 / f16 host tensor (pinned when allocated here).
+        Chunks ride a `HostPipeline` ring: upload -> ONE fused launch per chunk -> download.  Enqueue-only: synchronise the
+        current stream of the pipeline's device before reading the result."""
+        from . import imgproc
+
+        t = host_frames
+        if t.is_cuda:
+            raise PreprocessError("NotDeviceImage", "run_raw_host takes host frames; use run_raw_batch / run_raw_strided for device frames")
+        if t.dtype != torch.uint8 or t.dim() != 2 or not t.is_contiguous():
+            raise PreprocessError("InvalidRawSource", "host frames must be a contiguous [N, frame_bytes] uint8 tensor")
+        n, stride = t.shape
+        self._validate_raw(stride, src_w, src_h)
+        dw, dh = dst_size
+        want = torch.float16 if f16 else torch.float32
+        if out is None:
+            out = torch.empty((n, 3, dh, dw), dtype=want, pin_memory=True)
+        if out.is_cuda or out.dtype != want or not out.is_contiguous() or tuple(out.shape) != (n, 3, dh, dw):
+            raise PreprocessError("BadOutputShape", f"destination must be a contiguous host {want} tensor of shape {[n, 3, dh, dw]}")
+        fmt = self._fmt
+        desc = self._desc(src_w, src_h, fmt.pitch(src_w), fmt.bpp(), fmt.fmt_code(), dw, dh)
+        pipe = imgproc._pipeline_for(pipeline)
+        _lib.set_device(pipe.device.index)
+        st = _lib.lib().kb200_preprocess_host(pipe._h, torch.cuda.current_stream(pipe.device).cuda_stream, C.byref(desc), t.data_ptr(), t.numel(),
+                                             stride, n, out.data_ptr(), out.numel(), 1 if f16 else 0)
+        if st != _lib.OK:
+            kind = {_lib.ERR_INVALID_SOURCE: "InvalidRawSource"}.get(st, "Cuda")
+            raise PreprocessError(kind, _lib.last_error())
+        return out
+
     def run_raw_strided(self, base: torch.Tensor, frame_stride: int, batch: int, src_w: int, src_h: int,
                         dst: torch.Tensor, f16: bool = False) -> None:
         """Frames at `base + i*frame_stride` bytes (a capture ring buffer): no pointer table."""

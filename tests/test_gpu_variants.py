@@ -526,3 +526,24 @@ def test_undistort_pipeline_map_then_remap(kb, oracle, dev):
     dst = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev)
     kb.imgproc.remap(kb.Image(cu(src, dev)), dst, mx, my, kb.InterpolationMode.Bilinear)
     assert_f32_equal(dst.numpy(), oracle.remap(src, ox, oy, oracle.BILINEAR), "undistort f32")
+
+
+# ── host-buffer form of the camera preprocess (kb200_preprocess_host) ────────────
+@pytest.mark.parametrize("fmt,mode,dw,dh", [("Nv12", "Stretch", 192, 108), ("Nv12", "Letterbox", 64, 64), ("Yuyv", "Letterbox", 100, 60), ("Rgb8", "Stretch", 77, 41)])
+@pytest.mark.parametrize("f16", [False, True])
+def test_preprocess_host_pipeline(kb, oracle, dev, fmt, mode, dw, dh, f16):
+    """Host frames in / host tensor out must equal the device-buffer path bit for bit, across chunk boundaries of a small
+    staging ring (several chunks per call, ring depth 2)."""
+    w, h, n = 192, 108, 7
+    nbytes = {"Nv12": w * h * 3 // 2, "Yuyv": w * h * 2, "Rgb8": w * h * 3}[fmt]
+    host = torch.from_numpy(np.stack([raw_bytes(nbytes, k) for k in range(n)])).pin_memory()
+    pre = (kb.Preprocessor.builder().source_format(kb.SourceFormat[fmt]).mode(kb.ResizeMode[mode]).normalize(kb.Normalize.imagenet()).build_cuda())
+    want = torch.zeros((n, 3, dh, dw), dtype=torch.float16 if f16 else torch.float32, device=dev)
+    (pre.run_raw_batch_f16 if f16 else pre.run_raw_batch)([host[i].to(dev) for i in range(n)], w, h, want)
+    pipe = kb.imgproc.HostPipeline(dev, src_chunk_bytes=3 * ((nbytes + 15) // 16 * 16), dst_chunk_bytes=3 * 3 * dw * dh * 4, depth=2)
+    got = pre.run_raw_host(host, w, h, (dw, dh), f16=f16, pipeline=pipe)
+    torch.cuda.synchronize()
+    h2d, d2h = pipe.last_transfer()
+    assert h2d == n * nbytes and d2h == n * 3 * dw * dh * (2 if f16 else 4)
+    assert torch.equal(got.view(torch.int16 if f16 else torch.int32), want.cpu().view(torch.int16 if f16 else torch.int32))
+    pipe.close()
