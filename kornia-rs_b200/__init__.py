@@ -16,7 +16,7 @@ from . import _lib
 
 _lib.lib()  # fail loudly at import when libkornia_b200.so is absent
 
-from . import dist, imgproc  # noqa: E402
+from . import dist, fusion, imgproc  # noqa: E402
 from .image import Image, ImageError, ImageSize, InterpolationMode  # noqa: E402
 from .preprocess import (  # noqa: E402
     IMAGENET_MEAN,
@@ -48,7 +48,7 @@ def device_info() -> dict:
 
 
 __all__ = [
-    "Image", "ImageError", "ImageSize", "InterpolationMode", "imgproc", "dist", "Preprocessor", "PreprocessorBuilder",
+    "Image", "ImageError", "ImageSize", "InterpolationMode", "imgproc", "dist", "fusion", "Preprocessor", "PreprocessorBuilder",
     "PreprocessError", "ResizeMode", "Normalize", "SourceFormat", "PitchedSurface", "IMAGENET_MEAN", "IMAGENET_STD",
     "native_version", "device_info",
 ]

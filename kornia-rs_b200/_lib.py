@@ -51,6 +51,7 @@ def _declare(l: C.CDLL) -> None:
         "kb200_resize_lanczos_scratch_len": ([u32, u32, u32, u32], sz),
         "kb200_resize_lanczos_f32_c3": ([vp, vp, sz, vp, sz, vp, sz, u32, u32, u32, u32, u32], i),
         "kb200_generate_correction_map_polynomial": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_double), u32, u32, vp, vp, sz], i),
+        "kb200_fused_pipeline_u8_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32, u32, i, fp, fp, i], i),
         "kb200_pyrdown_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32], i),
         "kb200_pyrup_f32": ([vp, vp, sz, vp, sz, u32, u32, u32, u32], i),
         "kb200_pyrdown_u8": ([vp, vp, sz, vp, sz, u32, u32, u32, u32], i),

@@ -8,6 +8,7 @@
 // Per pixel: 8 B of map + the taps + the output; taps of neighbouring pixels overlap for smooth maps, so L1 serves
 // most of them.  Thread per destination pixel, map reads lane-contiguous.
 #include "kb200_common.cuh"
+#include "u8_sampler.cuh"
 
 namespace kb200 {
 
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) remap_f32_c3_kernel(const float* __restri
 
 template <int C, bool BILINEAR>
 __global__ void __launch_bounds__(256) remap_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const float* __restrict__ map_x,
-                                                       const float* __restrict__ map_y, int sw, int sh, uint32_t npx) {
+                                                       const float* __restrict__ map_y, int sw, int sh, uint32_t npx, bool words) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npx) return;
     const uint8_t* s = src + (size_t)blockIdx.y * sw * sh * C;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) remap_u8_kernel(const uint8_t* __restrict
     const uint32_t fx = __float2uint_rz((xf - (float)xi) * 1024.0f), fy = __float2uint_rz((yf - (float)yi) * 1024.0f);
     const uint32_t fx1 = 1024u - fx, fy1 = 1024u - fy;
     const int xi1 = (xi + 1 < sw) ? xi + 1 : xi, yi1 = (yi + 1 < sh) ? yi + 1 : yi;
+    if (C == 3 && words && q10_blend_c3_words(s, (uint32_t)sw * (uint32_t)sh * 3u, sw, xi, yi, xi1, yi1, fx, fy, d)) return;
     const uint8_t* r0 = s + (size_t)yi * sw * C;
     const uint8_t* r1 = s + (size_t)yi1 * sw * C;
 #pragma unroll
@@ -126,10 +128,11 @@ KB200_API int kb200_remap_u8(kb200_stream_t stream, const uint8_t* src, size_t s
     dim3 grid(div_up(npx, 256u), batch);
     cudaStream_t s = as_stream(stream);
     const bool bil = interp == KB200_INTERP_BILINEAR;
+    const bool words = C == 3 && knob(KNOB_B) != 1 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0 && (batch == 1 || ((size_t)sw * sh * 3) % 4 == 0);
 #define KB200_REMAP_U8(CC)                                                                                         \
     if (C == CC) {                                                                                                 \
-        if (bil) remap_u8_kernel<CC, true><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx);     \
-        else remap_u8_kernel<CC, false><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx);        \
+        if (bil) remap_u8_kernel<CC, true><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx, words);     \
+        else remap_u8_kernel<CC, false><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx, words);        \
     }
     KB200_REMAP_U8(1) KB200_REMAP_U8(3) KB200_REMAP_U8(4)
 #undef KB200_REMAP_U8

@@ -1765,3 +1765,41 @@ KO_API void ko_generate_correction_map_polynomial(const double intr[4], const do
             map_y[y * w + x] = (float)o[1];
         }
 }
+
+// ─────────────────────────────────────────────────────────────────────────────
+// §8(f) #3: the cuda/fusion.rs stage vocabulary — ReadU8RgbBilinear (:520-585: half-pixel `a*d + b`, max(0),
+// weights first, four-term sum), Normalize (:592-620: v*s + b), RgbToGray (:624-642: 0.299x + 0.587y + 0.114z
+// replicated to all three lanes), WriteChwF32 / WriteC1F32 (:645-690).  Restates the generated kernel body (and the
+// tests' own `cpu_reference`, :705-760).  maps: 0 none, 1 Normalize, 2 RgbToGray, 3 Normalize->RgbToGray,
+// 4 RgbToGray->Normalize.  sink: 0 CHW (3 planes), 1 C1 (the .x lane).
+// ─────────────────────────────────────────────────────────────────────────────
+KO_API int ko_fused_pipeline_u8(const uint8_t* src, size_t sw, size_t sh, size_t dw, size_t dh, int maps, const float scale[3],
+                                const float bias[3], int sink, float* dst) {
+    if (maps < 0 || maps > 4 || sink < 0 || sink > 1) return -1;
+    const float ax = (float)sw / (float)dw, ay = (float)sh / (float)dh;
+    const float bx = 0.5f * ax - 0.5f, by = 0.5f * ay - 0.5f;
+    const size_t plane = dw * dh;
+    for (size_t y = 0; y < dh; ++y)
+        for (size_t x = 0; x < dw; ++x) {
+            const float sxf = std::max(ax * (float)x + bx, 0.0f), syf = std::max(ay * (float)y + by, 0.0f);
+            const size_t sx0 = std::min((size_t)sxf, sw - 1), sy0 = std::min((size_t)syf, sh - 1);
+            const size_t sx1 = std::min(sx0 + 1, sw - 1), sy1 = std::min(sy0 + 1, sh - 1);
+            const float wx = sxf - (float)sx0, wy = syf - (float)sy0;
+            const float w00 = (1.0f - wy) * (1.0f - wx), w01 = (1.0f - wy) * wx, w10 = wy * (1.0f - wx), w11 = wy * wx;
+            float v[3];
+            for (int c = 0; c < 3; ++c) {
+                auto p = [&](size_t yy, size_t xx) { return (float)src[(yy * sw + xx) * 3 + c]; };
+                v[c] = w00 * p(sy0, sx0) + w01 * p(sy0, sx1) + w10 * p(sy1, sx0) + w11 * p(sy1, sx1);
+            }
+            auto norm = [&]() { for (int c = 0; c < 3; ++c) v[c] = v[c] * scale[c] + bias[c]; };
+            auto gray = [&]() { const float g = 0.299f * v[0] + 0.587f * v[1] + 0.114f * v[2]; v[0] = v[1] = v[2] = g; };
+            if (maps == 1) norm();
+            else if (maps == 2) gray();
+            else if (maps == 3) { norm(); gray(); }
+            else if (maps == 4) { gray(); norm(); }
+            const size_t di = y * dw + x;
+            if (sink == 0) { dst[di] = v[0]; dst[di + plane] = v[1]; dst[di + 2 * plane] = v[2]; }
+            else dst[di] = v[0];
+        }
+    return 0;
+}

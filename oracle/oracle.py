@@ -599,3 +599,15 @@ def generate_correction_map_polynomial(intrinsic, distortion, w: int, h: int):
     f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]; f.restype = None
     f(_p(intr), _p(dist), w, h, _p(mx), _p(my))
     return mx, my
+
+
+# ── cuda/fusion.rs stage vocabulary ──────────────────────────────────────────
+def fused_pipeline_u8(src: np.ndarray, dw: int, dh: int, maps: int, scale=(1.0, 1.0, 1.0), bias=(0.0, 0.0, 0.0), sink: int = 0) -> np.ndarray:
+    """maps: 0 none, 1 Normalize, 2 RgbToGray, 3 Normalize->RgbToGray, 4 RgbToGray->Normalize; sink 0 = CHW, 1 = single plane."""
+    src = np.ascontiguousarray(src, np.uint8)
+    sh, sw, _ = src.shape
+    dst = np.empty((3, dh, dw) if sink == 0 else (1, dh, dw), np.float32)
+    f = lib().ko_fused_pipeline_u8
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]; f.restype = C.c_int
+    assert f(_p(src), sw, sh, dw, dh, maps, _p(_f3(scale)), _p(_f3(bias)), sink, _p(dst)) == 0
+    return dst

@@ -547,3 +547,36 @@ def test_preprocess_host_pipeline(kb, oracle, dev, fmt, mode, dw, dh, f16):
     assert h2d == n * nbytes and d2h == n * 3 * dw * dh * (2 if f16 else 4)
     assert torch.equal(got.view(torch.int16 if f16 else torch.int32), want.cpu().view(torch.int16 if f16 else torch.int32))
     pipe.close()
+
+
+# ── cuda/fusion.rs stage vocabulary as pre-instantiated pipelines ────────────────
+@pytest.mark.parametrize("chain,code", [("", 0), ("N", 1), ("G", 2), ("NG", 3), ("GN", 4)])
+@pytest.mark.parametrize("sink", [0, 1])
+def test_fused_pipelines(kb, oracle, dev, chain, code, sink):
+    """cuda/fusion.rs:762-840 (`fused_resize_normalize_chw_matches_cpu`, `fused_novel_gray_chain`): every composable shape,
+    batched, against the restated generated kernel; the reference's own tolerance is 1e-4 relative — here bit equality."""
+    from kornia_rs_b200.fusion import FusedPipeline, Normalize, ReadU8RgbBilinear, RgbToGray, WriteC1F32, WriteChwF32
+    sw, sh, dw, dh, n = 100, 80, 47, 33, 3
+    src = np.stack([oracle.pattern_u8(sw * sh * 3, 11 + i).reshape(sh, sw, 3) for i in range(n)])
+    scale, bias = [1.0 / 255.0, 0.5 / 255.0, 2.0 / 255.0], [0.1, -0.2, 0.05]
+    stages = [ReadU8RgbBilinear(sw, sh, dw, dh)] + [Normalize(scale, bias) if k == "N" else RgbToGray() for k in chain] + [WriteChwF32() if sink == 0 else WriteC1F32()]
+    pipe = FusedPipeline.build(stages, dw, dh)
+    dst = torch.zeros((n, pipe.out_planes(), dh, dw), dtype=torch.float32, device=dev)
+    pipe.launch(cu(src, dev), dst)
+    assert last_kernel(kb) == "fused_pipeline_kernel"
+    want = np.stack([oracle.fused_pipeline_u8(src[i], dw, dh, code, scale, bias, sink) for i in range(n)])
+    assert_f32_equal(dst.cpu().numpy(), want, f"fusion chain '{chain}' sink {sink}")
+
+
+def test_fused_pipeline_shape_errors(kb, dev):
+    from kornia_rs_b200.fusion import FusedPipeline, FusionError, Normalize, ReadU8RgbBilinear, RgbToGray, WriteChwF32
+    read = ReadU8RgbBilinear(64, 64, 32, 32)
+    with pytest.raises(FusionError, match="at least a source and a sink"):
+        FusedPipeline.build([read], 32, 32)
+    with pytest.raises(FusionError, match="first stage must be a source"):
+        FusedPipeline.build([RgbToGray(), WriteChwF32()], 32, 32)
+    with pytest.raises(FusionError, match="not a pre-instantiated shape"):
+        FusedPipeline.build([read, RgbToGray(), RgbToGray(), WriteChwF32()], 32, 32)
+    pipe = FusedPipeline.build([read, Normalize([1, 1, 1], [0, 0, 0]), WriteChwF32()], 32, 32)
+    with pytest.raises(FusionError, match="destination holds"):
+        pipe.launch(torch.zeros((64, 64, 3), dtype=torch.uint8, device=dev), torch.zeros((3, 16, 16), dtype=torch.float32, device=dev))
