@@ -137,6 +137,29 @@ pub mod ffi {
         pub fn kb200_preprocess_strided_f32(stream: *mut c_void, desc: *const kb200_preprocess_desc, base: *const u8, base_len: usize, frame_stride: usize, batch: u32, dst: *mut f32, dst_len: usize) -> c_int;
         pub fn kb200_preprocess_strided_f16(stream: *mut c_void, desc: *const kb200_preprocess_desc, base: *const u8, base_len: usize, frame_stride: usize, batch: u32, dst: *mut u16, dst_len: usize) -> c_int;
         pub fn kb200_selftest_div255(stream: *mut c_void, mismatches_dev: *mut u64) -> c_int;
+
+        // round 2: bicubic / Lanczos resize, pyramids, undistort maps, fusion pipelines, host-buffer preprocess
+        pub fn kb200_resize_bicubic_f32_c3(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize, src_w: u32,
+                                           src_h: u32, dst_w: u32, dst_h: u32, batch: u32) -> c_int;
+        pub fn kb200_resize_lanczos_scratch_len(src_h: u32, dst_w: u32, dst_h: u32, batch: u32) -> usize;
+        pub fn kb200_resize_lanczos_f32_c3(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize,
+                                           scratch: *mut f32, scratch_len: usize, src_w: u32, src_h: u32, dst_w: u32, dst_h: u32, batch: u32) -> c_int;
+        pub fn kb200_pyrdown_f32(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize, src_w: u32, src_h: u32,
+                                 channels: u32, batch: u32) -> c_int;
+        pub fn kb200_pyrup_f32(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize, src_w: u32, src_h: u32,
+                               channels: u32, batch: u32) -> c_int;
+        pub fn kb200_pyrdown_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32, src_h: u32,
+                                channels: u32, batch: u32) -> c_int;
+        pub fn kb200_pyrup_u8(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut u8, dst_len: usize, src_w: u32, src_h: u32,
+                              channels: u32, batch: u32) -> c_int;
+        pub fn kb200_generate_correction_map_polynomial(stream: *mut c_void, intrinsic: *const f64, distortion: *const f64, width: u32,
+                                                        height: u32, map_x: *mut f32, map_y: *mut f32, map_len: usize) -> c_int;
+        pub fn kb200_fused_pipeline_u8_f32(stream: *mut c_void, src: *const u8, src_len: usize, dst: *mut f32, dst_len: usize, src_w: u32,
+                                           src_h: u32, dst_w: u32, dst_h: u32, batch: u32, maps: c_int, scale: *const f32, bias: *const f32,
+                                           sink: c_int) -> c_int;
+        pub fn kb200_preprocess_host(pipeline: *mut kb200_host_pipeline, stream: *mut c_void, desc: *const kb200_preprocess_desc,
+                                     host_base: *const u8, base_len: usize, frame_stride: usize, batch: u32, host_dst: *mut c_void,
+                                     dst_len: usize, out_f16: c_int) -> c_int;
     }
 }
 

@@ -320,3 +320,17 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_rust_binding_covers_the_header():
+    """bindings/rust/src/lib.rs cannot be compiled here (no Rust toolchain): at least keep its `extern "C"` block in
+    lock-step with include/kornia_b200.h — every declared entry point has an FFI declaration, and nothing extra."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "kornia_b200.h")).read()
+    rs = open(os.path.join(root, "bindings", "rust", "src", "lib.rs")).read()
+    declared = set(re.findall(r"KB200_API\s+[\w\s\*]+?\b(kb200_\w+)\s*\(", hdr))
+    ffi = set(re.findall(r"pub fn (kb200_\w+)\s*\(", rs.split("extern \"C\" {", 1)[1].split("\n    }\n", 1)[0]))
+    assert declared - ffi == set(), f"missing in the Rust FFI block: {sorted(declared - ffi)}"
+    assert ffi - declared == set(), f"not in the header: {sorted(ffi - declared)}"
+    assert "#[repr(C)]\n    #[derive(Clone, Copy, Debug, Default)]\n    pub struct kb200_preprocess_desc" in rs   # ADVICE r1: repr(C) on the descriptor
