@@ -609,5 +609,6 @@ def fused_pipeline_u8(src: np.ndarray, dw: int, dh: int, maps: int, scale=(1.0, 
     dst = np.empty((3, dh, dw) if sink == 0 else (1, dh, dw), np.float32)
     f = lib().ko_fused_pipeline_u8
     f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]; f.restype = C.c_int
-    assert f(_p(src), sw, sh, dw, dh, maps, _p(_f3(scale)), _p(_f3(bias)), sink, _p(dst)) == 0
+    sc, bi = _f3(scale), _f3(bias)      # keep the arrays alive across the call
+    assert f(_p(src), sw, sh, dw, dh, maps, _p(sc), _p(bi), sink, _p(dst)) == 0
     return dst
