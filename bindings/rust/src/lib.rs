@@ -137,6 +137,7 @@ pub mod ffi {
         pub fn kb200_preprocess_strided_f32(stream: *mut c_void, desc: *const kb200_preprocess_desc, base: *const u8, base_len: usize, frame_stride: usize, batch: u32, dst: *mut f32, dst_len: usize) -> c_int;
         pub fn kb200_preprocess_strided_f16(stream: *mut c_void, desc: *const kb200_preprocess_desc, base: *const u8, base_len: usize, frame_stride: usize, batch: u32, dst: *mut u16, dst_len: usize) -> c_int;
         pub fn kb200_selftest_div255(stream: *mut c_void, mismatches_dev: *mut u64) -> c_int;
+        pub fn kb200_selftest_div2(stream: *mut c_void, count: u64, seed: u32, mismatches_dev: *mut u64) -> c_int;
 
         // round 2: bicubic / Lanczos resize, pyramids, undistort maps, fusion pipelines, host-buffer preprocess
         pub fn kb200_resize_bicubic_f32_c3(stream: *mut c_void, src: *const f32, src_len: usize, dst: *mut f32, dst_len: usize, src_w: u32,

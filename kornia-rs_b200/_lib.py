@@ -99,6 +99,7 @@ def _declare(l: C.CDLL) -> None:
         "kb200_std_mean_finalize": ([C.POINTER(C.c_uint64), sz, C.POINTER(C.c_double), C.POINTER(C.c_double)], None),
         "kb200_preprocess_affine": ([i, u32, u32, u32, u32, fp], None),
         "kb200_selftest_div255": ([vp, vp], i),
+        "kb200_selftest_div2": ([vp, C.c_uint64, C.c_uint32, vp], i),
         "kb200_preprocess_src_bytes": ([C.POINTER(PreprocessDesc)], sz),
         "kb200_preprocess_f32": ([vp, C.POINTER(PreprocessDesc), C.POINTER(vp), C.POINTER(sz), u32, vp, sz], i),
         "kb200_preprocess_f16": ([vp, C.POINTER(PreprocessDesc), C.POINTER(vp), C.POINTER(sz), u32, vp, sz], i),

@@ -580,3 +580,13 @@ def test_fused_pipeline_shape_errors(kb, dev):
     pipe = FusedPipeline.build([read, Normalize([1, 1, 1], [0, 0, 0]), WriteChwF32()], 32, 32)
     with pytest.raises(FusionError, match="destination holds"):
         pipe.launch(torch.zeros((64, 64, 3), dtype=torch.uint8, device=dev), torch.zeros((3, 16, 16), dtype=torch.float32, device=dev))
+
+
+def test_shared_reciprocal_division_is_exact(kb, dev):
+    """warp_div2 (one reciprocal for the two perspective quotients) must equal two IEEE divisions bit for bit: 2^31 random
+    operand triples over a wide exponent range + zero / denormal / window-edge cases, compared on the device."""
+    mism = torch.zeros(1, dtype=torch.int64, device=dev)
+    for seed in (1, 77):
+        st = kb._lib.lib().kb200_selftest_div2(torch.cuda.current_stream(dev).cuda_stream, 1 << 30, seed, mism.data_ptr())
+        assert st == 0, kb._lib.last_error()
+        assert int(mism.item()) == 0, f"{int(mism.item())} operand triples differ from __fdiv_rn (seed {seed})"

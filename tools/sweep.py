@@ -52,8 +52,8 @@ if what == "warp":
     fn = lambda: kb.imgproc.warp_perspective(src, dst, H, kb.InterpolationMode.Bilinear)
     alg = n * w * h * 24
     setk(warp_path=1)
-    for a in (1, 0):
-        for pf in (0, 64, 96, 192, 256, -1):
+    for a in (1, 0):      # a = 1: two __fdiv_rn; a = 0: shared reciprocal
+        for pf in (0, 96, -1):
             setk(a=a, warp_pf=pf)
             ms = timeit(fn)
             print(f"gather pf_all={a} pf={pf:3d} {kb._lib.last_kernel():28s} {ms:.4f} ms  frac {alg / ms / 1e6 / PEAK:.3f}", flush=True)
