@@ -506,24 +506,27 @@ int launch_fused_resize_rows(cudaStream_t s, const uint8_t* src, float* dst, con
     if ((row_bytes & 15u) || !aligned16(src) || p.scale_x > 6.0f || p.sw < 16u) return KB200_OK;
     // developer knobs (tuning sweeps only, kb200_debug_set_knob): fr.npx, fr.stages, fr.ctas
     const int tune_npx = knob(KNOB_FR_NPX), tune_stages = knob(KNOB_FR_STAGES), tune_ctas = knob(KNOB_FR_CTAS);
-    // columns per thread: least padding in the last tile (within 2 %); among equals prefer 2, then 3, 1, 4, 5 — the
-    // B200 sweep (profiles/r1_cfg2_fused_resize.md) has 2 columns/thread ahead: enough amortisation, many producers.
-    int npx = 1;
-    {
-        static const int order[5] = {2, 3, 1, 4, 5};
-        double best = 1e30;
-        for (int i = 0; i < 5; ++i) {
-            const uint32_t tw = FR_CT * order[i];
-            const double waste = (double)((p.dw + tw - 1) / tw) * tw / (double)p.dw;
-            if (waste < best - 0.02) { best = waste; npx = order[i]; }
-        }
-        if (tune_npx >= 1 && tune_npx <= 5) npx = tune_npx;
-    }
-    const uint32_t TW = FR_CT * (uint32_t)npx;
     const bool yz = axis_weights_all_zero(p.dh, p.sh, p.scale_y);
     const bool xz = yz && axis_weights_all_zero(p.dw, p.sw, p.scale_x);
     const bool box2x = (p.sw == 2 * p.dw && p.sh == 2 * p.dh);
     const int mode = box2x ? FR_BOX : (xz ? FR_POINT : (yz ? FR_YZERO : FR_GENERAL));
+    // columns per thread: least padding in the last tile; among near-equals prefer 2, then 3, 1, 4, 5 — the B200 sweep
+    // (profiles/r1_cfg2_fused_resize.md) has 2 columns/thread ahead: enough amortisation, many producers.  The general
+    // mode (two source rows and a full lerp per pixel) is heavier per pixel: it accepts up to 10 % tile padding to keep
+    // >= 2 columns per thread (round-2 sweep, 4K -> 1600x900: npx 1 0.130 ms, npx 2 0.104 ms at 4 CTAs x 4 stages).
+    int npx = 1;
+    {
+        static const int order[5] = {2, 3, 1, 4, 5};
+        const double tol = mode == FR_GENERAL ? 0.10 : 0.02;
+        double best = 1e30;
+        for (int i = 0; i < 5; ++i) {
+            const uint32_t tw = FR_CT * order[i];
+            const double waste = (double)((p.dw + tw - 1) / tw) * tw / (double)p.dw;
+            if (waste < best - tol) { best = waste; npx = order[i]; }
+        }
+        if (tune_npx >= 1 && tune_npx <= 5) npx = tune_npx;
+    }
+    const uint32_t TW = FR_CT * (uint32_t)npx;
     // span bound: x0(last) - x0(first) <= ceil((TW-1)*scale_x) + 1 pixels, + the +1 tap, + 16-B rounding both ends
     const double span_px = (double)(TW - 1) * (double)p.scale_x + 4.0;
     uint32_t slot = (uint32_t)(span_px * 3.0) + 32u;
@@ -532,8 +535,8 @@ int launch_fused_resize_rows(cudaStream_t s, const uint8_t* src, float* dst, con
     const uint32_t stage_bytes = slot * ((mode == FR_GENERAL || mode == FR_BOX) ? 2u : 1u);
     // Ring sizing: the sweep's optimum keeps ~36 KB of source rows in flight per SM (about bandwidth x latency for the
     // whole GPU); deeper rings or more CTAs than that cost 5-8 % (queueing in the memory system), fewer starve.
-    uint32_t stages = tune_stages >= 2 && tune_stages <= FR_MAX_STAGES ? (uint32_t)tune_stages : 3u;
-    int per_sm = tune_ctas > 0 ? tune_ctas : (int)std::lround(36.0 * 1024.0 / ((double)stages * stage_bytes));
+    uint32_t stages = tune_stages >= 2 && tune_stages <= FR_MAX_STAGES ? (uint32_t)tune_stages : (mode == FR_GENERAL ? 4u : 3u);
+    int per_sm = tune_ctas > 0 ? tune_ctas : (mode == FR_GENERAL ? 4 : (int)std::lround(36.0 * 1024.0 / ((double)stages * stage_bytes)));
     per_sm = std::max(2, std::min(per_sm, 8));
     while (per_sm > 2 && (size_t)per_sm * ((size_t)stages * stage_bytes + 1024) > 200 * 1024) --per_sm;
     if (tune_ctas <= 0 && tune_stages <= 0 && per_sm == 2) stages = std::min<uint32_t>(FR_MAX_STAGES, std::max<uint32_t>(3u, (uint32_t)(18.0 * 1024.0 / stage_bytes)));
