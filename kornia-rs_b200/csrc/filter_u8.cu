@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kb200_common.cuh"
+#include "tma_ring.cuh"
 
 namespace kb200 {
 
@@ -227,6 +228,190 @@ __global__ void __launch_bounds__(256) blur_u8_tile_w_kernel(const uint8_t* __re
     }
 }
 
+// ── row-streaming variant (round 2) ───────────────────────────────────────────────────────────
+// The tile kernel above pays two block-wide phase changes, a (64+K-1)^2 / 64^2 halo and a shared-memory round trip of the
+// intermediate per tile: 0.23 of the roofline.  This is the u8 twin of sep_filter_stream2 (filter.cu): a unit is
+// (image, strip of 128*NV words of a row, chunk of rows); every source row span is copied ONCE global -> shared by the
+// TMA engine (cp.async.bulk, mbarrier ring, producer lane; rows clamped = the reference's replicate border in y); a
+// consumer thread owns NV word columns: the H pass reads the words around its column (compile-time funnel shifts per tap,
+// two 16-bit lanes per register as above), its u8x4 result goes into a K-deep REGISTER window (row loop unrolled K times),
+// and as soon as the window is full the V pass emits one lane-contiguous STG.32 per column.  The u8 intermediate never
+// leaves registers; no __syncthreads in the loop.  Only the few threads whose taps cross the left / right image border
+// take a byte-wise path with clamped column indices (the replicate border in x).
+// Needs rows of a multiple of 16 bytes and 16-byte aligned images (TMA); anything else uses the tile kernels.
+static constexpr int U8S_CT = 128, U8S_THREADS = U8S_CT + 32, U8S_MAX_STAGES = 16, U8S_HALO = 16;
+
+struct U8StreamParams {
+    uint32_t rowb, rows, strips, chunks, rows_per_chunk, nunits, stages, slot_bytes;
+};
+
+__device__ __forceinline__ uint32_t u8s_q8_lanes(const uint32_t (&x)[7], const uint32_t (&k)[7], int n) {
+    uint32_t ae = 0x00800080u, ao = 0x00800080u;         // + 128 per 16-bit lane
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+        if (t >= n) break;
+        ae += (x[t] & 0x00FF00FFu) * k[t];
+        ao += ((x[t] >> 8) & 0x00FF00FFu) * k[t];
+    }
+    return ((ae >> 8) & 0x00FF00FFu) | (ao & 0xFF00FF00u);
+}
+
+template <int C, int K, int NV>
+__global__ void __launch_bounds__(U8S_THREADS) blur_u8_stream_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                     const __grid_constant__ U8Taps T, const __grid_constant__ U8StreamParams P) {
+    constexpr int HX = K / 2, HY = K / 2;
+    constexpr int EB = U8S_CT * NV * 4;                       // bytes of a strip
+    static_assert(HX * C <= U8S_HALO, "halo");
+    extern __shared__ __align__(128) uint8_t u8s_smem[];
+    __shared__ __align__(8) uint64_t full_bar[U8S_MAX_STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[U8S_MAX_STAGES];
+    const uint32_t tid = threadIdx.x, nst = P.stages;
+    if (tid == 0) {
+        for (uint32_t s = 0; s < nst; ++s) { tma::mbar_init(&full_bar[s], 1); tma::mbar_init(&empty_bar[s], U8S_CT / 32); }
+        tma::mbar_fence_init();
+    }
+    __syncthreads();
+    const size_t img_bytes = (size_t)P.rowb * P.rows;
+    uint32_t stage = 0, phase = 0;
+
+    if (tid >= U8S_CT) {
+        if (tid != U8S_CT) return;
+        bool first_lap = true;
+        for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
+            const uint32_t strip = u % P.strips, rest = u / P.strips;
+            const uint32_t chunk = rest % P.chunks, img = rest / P.chunks;
+            const int e0 = (int)(strip * EB);
+            const int g0 = max(e0 - U8S_HALO, 0), g1 = min(e0 + EB + U8S_HALO, (int)P.rowb);   // multiples of 16
+            const uint32_t bytes = (uint32_t)(g1 - g0);
+            const uint32_t slot_off = (uint32_t)(g0 - (e0 - U8S_HALO));
+            const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
+            const uint8_t* base = src + (size_t)img * img_bytes + g0;
+            for (int iy = y_first - HY; iy < y_end + HY; ++iy) {
+                if (!first_lap) tma::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                const int sy = min(max(iy, 0), (int)P.rows - 1);          // replicate border in y: the clamped row (filter/ops.rs:852-1100)
+                tma::mbar_expect_tx(&full_bar[stage], bytes);
+                tma::load_1d(u8s_smem + (size_t)stage * P.slot_bytes + slot_off, base + (size_t)sy * P.rowb, bytes, &full_bar[stage]);
+                if (++stage == nst) { stage = 0; phase ^= 1u; first_lap = false; }
+            }
+        }
+        return;
+    }
+
+    uint32_t kx[7], ky[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { kx[k] = k < K ? T.kx[k] : 0u; ky[k] = k < K ? T.ky[k] : 0u; }
+    const bool binomial = T.binomial != 0;
+    const bool lane0 = (tid & 31u) == 0;
+    const int cols = (int)(P.rowb / C);
+    for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
+        const uint32_t strip = u % P.strips, rest = u / P.strips;
+        const uint32_t chunk = rest % P.chunks, img = rest / P.chunks;
+        const int e0 = (int)(strip * EB);
+        const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
+        uint8_t* out = dst + (size_t)img * img_bytes + (size_t)y_first * P.rowb;
+        int B[NV];            // first global byte (within the row) of this thread's word column v
+        bool act[NV], edge[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            B[v] = e0 + 4 * ((int)tid + v * U8S_CT);
+            act[v] = B[v] < (int)P.rowb;
+            edge[v] = B[v] - HX * C < 0 || B[v] + 3 + HX * C >= (int)P.rowb;     // taps cross the left / right border: clamp per byte
+        }
+        uint32_t win[K][NV];
+        int iy = y_first - HY;
+        const int iy_end = y_end + HY;
+        while (iy < iy_end) {
+#pragma unroll
+            for (int s = 0; s < K; ++s) {          // unrolled: window slot indices are compile-time
+                if (iy >= iy_end) break;
+                tma::mbar_wait(&full_bar[stage], phase);
+                const uint8_t* slot = u8s_smem + (size_t)stage * P.slot_bytes;          // slot byte j = row byte e0 - 16 + j
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    uint32_t hres = 0;
+                    if (act[v]) {
+                        uint32_t x[7];
+                        if (!edge[v]) {
+                            // tap t of output bytes B..B+3 starts at row byte B + (t - HX)*C: word index and shift are
+                            // compile-time relative to this thread's word
+                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(slot) + (U8S_HALO / 4) + tid + v * U8S_CT;
+#pragma unroll
+                            for (int t = 0; t < 7; ++t) {
+                                if (t >= K) break;
+                                constexpr int dummy = 0; (void)dummy;
+                                const int off = (t - HX) * C;                           // byte offset, may be negative
+                                const int wi = (off >= 0) ? (off >> 2) : -((-off + 3) >> 2);
+                                const int sh = off - 4 * wi;                            // 0..3
+                                x[t] = sh == 0 ? wp[wi] : __funnelshift_r(wp[wi], wp[wi + 1], 8 * sh);
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 7; ++t) {
+                                if (t >= K) break;
+                                uint32_t w = 0;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int gb = B[v] + j, px = gb / C, ch = gb - px * C;
+                                    const int sx = min(max(px + t - HX, 0), cols - 1);    // replicate border in x
+                                    w |= (uint32_t)slot[sx * C + ch - (e0 - U8S_HALO)] << (8 * j);
+                                }
+                                x[t] = w;
+                            }
+                        }
+                        hres = binomial ? avg4_round_up(avg4_round_up(x[0], x[1]), avg4_round_up(x[1], x[2])) : u8s_q8_lanes(x, kx, K);
+                    }
+                    win[s][v] = hres;
+                }
+                __syncwarp();
+                if (lane0) tma::mbar_arrive(&empty_bar[stage]);
+                if (++stage == nst) { stage = 0; phase ^= 1u; }
+                // output row r = iy - HY is complete: its window is slots s+1 .. s+K (mod K), oldest first
+                if (iy - HY >= y_first) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        if (!act[v]) continue;
+                        uint32_t y[7];
+#pragma unroll
+                        for (int t = 0; t < 7; ++t) y[t] = t < K ? win[(s + 1 + t) % K][v] : 0u;
+                        const uint32_t o = binomial ? avg4_round_up(avg4_round_up(y[0], y[1]), avg4_round_up(y[1], y[2])) : u8s_q8_lanes(y, ky, K);
+                        *reinterpret_cast<uint32_t*>(out + B[v]) = o;
+                    }
+                    out += P.rowb;
+                }
+                ++iy;
+            }
+        }
+    }
+}
+
+template <int C, int K>
+static int launch_blur_u8_stream(cudaStream_t s, const uint8_t* src, uint8_t* dst, uint32_t cols, uint32_t rows, uint32_t batch, const U8Taps& T) {
+    constexpr int NV = 2;
+    auto kern = blur_u8_stream_kernel<C, K, NV>;
+    U8StreamParams P;
+    P.rowb = cols * C; P.rows = rows;
+    const uint32_t EB = U8S_CT * NV * 4;
+    P.strips = (P.rowb + EB - 1) / EB;
+    P.slot_bytes = EB + 2 * U8S_HALO + 32;                  // + slack: the last funnel shift reads one word past the halo
+    P.slot_bytes = (P.slot_bytes + 127u) & ~127u;
+    P.stages = 6;
+    const size_t smem = (size_t)P.slot_bytes * P.stages;
+    int resident = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, U8S_THREADS, smem) != cudaSuccess || resident < 1) { cudaGetLastError(); return 1; }
+    const int per_sm = std::min(resident, knob(KNOB_C) > 0 ? knob(KNOB_C) : 8);
+    const size_t ctas = (size_t)device_info().sm_count * per_sm;
+    const size_t total = (size_t)P.strips * batch * rows;
+    uint32_t rc = knob(KNOB_D) > 0 ? (uint32_t)knob(KNOB_D) : (uint32_t)std::max<size_t>(32, total / (ctas * 12));
+    rc = std::min(rc, rows);
+    P.rows_per_chunk = rc;
+    P.chunks = (rows + rc - 1) / rc;
+    const size_t nunits = (size_t)P.strips * P.chunks * batch;
+    if (nunits > 0x7FFFFFFFull) return 1;
+    P.nunits = (uint32_t)nunits;
+    kern<<<(unsigned)std::min<size_t>(nunits, ctas), U8S_THREADS, smem, s>>>(src, dst, T, P);
+    return check_launch("blur_u8_stream_kernel") == KB200_OK ? 0 : -1;
+}
+
 // filter/ops.rs:759-770
 static void quantize_kernel_256(const float* k, int n, uint8_t* out) {
     uint32_t sum = 0;
@@ -270,6 +455,18 @@ static int launch_blur_u8(cudaStream_t s, const uint8_t* src, size_t src_len, ui
         for (int k = 0; k < T.kyn; ++k) sy += T.ky[k];
         const bool word_ok = ((size_t)cols * C) % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 3u) == 0 &&
                              T.kxn == T.kyn && (T.binomial || (sx <= 256 && sy <= 256)) && cols >= 4;
+        // row-streaming kernel: additionally needs 16-byte rows / bases (TMA row copies) and rows long enough for a strip
+        const bool stream_ok = word_ok && (T.kxn == 3 || T.kxn == 5 || T.kxn == 7) && ((size_t)cols * C) % 16 == 0 && (size_t)cols * C >= 256 &&
+                               ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0 && (T.kxn / 2) * (int)C <= U8S_HALO &&
+                               knob(KNOB_B) != 3;
+        if (stream_ok) {
+            int r = 1;
+#define KB200_U8S(CC, KK) if (C == CC && T.kxn == KK) r = launch_blur_u8_stream<CC, KK>(s, src, dst, cols, rows, batch, T);
+            KB200_U8S(1, 3) KB200_U8S(1, 5) KB200_U8S(1, 7) KB200_U8S(3, 3) KB200_U8S(3, 5) KB200_U8S(3, 7) KB200_U8S(4, 3) KB200_U8S(4, 5) KB200_U8S(4, 7)
+#undef KB200_U8S
+            if (r == 0) return KB200_OK;
+            if (r < 0) return KB200_ERR_CUDA;
+        }
         if (word_ok && (T.kxn == 3 || T.kxn == 5 || T.kxn == 7)) {
             auto gow = [&](auto kern, int K) -> int {
                 const int hx = K / 2;

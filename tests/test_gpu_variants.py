@@ -590,3 +590,47 @@ def test_shared_reciprocal_division_is_exact(kb, dev):
         st = kb._lib.lib().kb200_selftest_div2(torch.cuda.current_stream(dev).cuda_stream, 1 << 30, seed, mism.data_ptr())
         assert st == 0, kb._lib.last_error()
         assert int(mism.item()) == 0, f"{int(mism.item())} operand triples differ from __fdiv_rn (seed {seed})"
+
+
+# ── u8 blurs: the row-streaming kernel (round 2) and the tile kernels, named ──────
+@pytest.mark.parametrize("cols,rows,c,n,k,sigma", [
+    (1376, 19, 3, 2, 5, 1.5),     # several strips (4128-byte rows), Q8 5x5
+    (3840, 40, 3, 1, 5, 1.5),     # the bench geometry's row length
+    (256, 40, 1, 2, 3, 0.8),      # binomial [1,2,1]/4 path, one partial strip
+    (256, 33, 1, 1, 7, 2.0),      # 7 taps
+    (640, 33, 4, 2, 7, 2.5),      # C = 4, 12-byte halo
+    (1024, 70, 4, 1, 3, 2.0),     # k = 3 outside the binomial sigma window -> Q8
+    (96, 300, 3, 1, 5, 1.2),      # one short strip (288-byte rows), many row chunks
+])
+def test_gaussian_blur_u8_stream(kb, oracle, dev, cols, rows, c, n, k, sigma):
+    assert (cols * c) % 16 == 0
+    src = np.stack([oracle.pattern_u8(rows * cols * c, 0x51 + i).reshape(rows, cols, c) for i in range(n)])
+    d = kb.Image(torch.full((n, rows, cols, c), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.gaussian_blur_u8(kb.Image(cu(src, dev)), d, (k, k), (sigma, sigma))
+    assert last_kernel(kb) == "blur_u8_stream_kernel", last_kernel(kb)
+    want = np.stack([oracle.gaussian_blur_u8(src[i], (k, k), (sigma, sigma)) for i in range(n)])
+    np.testing.assert_array_equal(d.numpy(), want)
+    # the tile kernel on the same input (knob b = 3 disables streaming) must agree too
+    kb._lib.set_knob("b", 3)
+    try:
+        d2 = kb.Image.zeros_cuda(kb.ImageSize(cols, rows), c, torch.uint8, dev, batch=n)
+        kb.imgproc.gaussian_blur_u8(kb.Image(cu(src, dev)), d2, (k, k), (sigma, sigma))
+        assert last_kernel(kb) in ("blur_u8_tile_w_kernel", "blur_u8_tile_kernel")
+    finally:
+        kb._lib.set_knob("b", 0)
+    np.testing.assert_array_equal(d2.numpy(), want)
+
+
+def test_box_blur_u8_stream_and_full_4k(kb, oracle, dev):
+    src = oracle.pattern_u8(64 * 512 * 3, 0x91).reshape(64, 512, 3)
+    d = kb.Image.zeros_cuda(kb.ImageSize(512, 64), 3, torch.uint8, dev)
+    kb.imgproc.box_blur_u8(kb.Image(cu(src, dev)), d, (5, 5))
+    assert last_kernel(kb) == "blur_u8_stream_kernel"
+    np.testing.assert_array_equal(d.numpy(), oracle.box_blur_u8(src, (5, 5)))
+    # the bench row at full size: 4K RGB u8, gaussian 5x5 sigma 1.5 — every byte
+    w, h = 3840, 2160
+    big = oracle.pattern_u8(w * h * 3, 0x92).reshape(h, w, 3)
+    d4 = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.uint8, dev)
+    kb.imgproc.gaussian_blur_u8(kb.Image(cu(big, dev)), d4, (5, 5), (1.5, 1.5))
+    assert last_kernel(kb) == "blur_u8_stream_kernel"
+    np.testing.assert_array_equal(d4.numpy(), oracle.gaussian_blur_u8(big, (5, 5), (1.5, 1.5)))
