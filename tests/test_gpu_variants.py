@@ -634,3 +634,24 @@ def test_box_blur_u8_stream_and_full_4k(kb, oracle, dev):
     kb.imgproc.gaussian_blur_u8(kb.Image(cu(big, dev)), d4, (5, 5), (1.5, 1.5))
     assert last_kernel(kb) == "blur_u8_stream_kernel"
     np.testing.assert_array_equal(d4.numpy(), oracle.gaussian_blur_u8(big, (5, 5), (1.5, 1.5)))
+
+
+@pytest.mark.parametrize("mode", ["Bilinear", "Nearest"])
+def test_warp_gather64_fallback(kb, oracle, dev, mode):
+    """The >= 2^31-element fallback (64-bit indexing) forced on a small image: same shared arithmetic, same bits."""
+    sw, sh = 129, 97
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3)
+    h = [1.03, 0.05, -3.0, -0.02, 0.97, 4.0, 2.0 / (97 * 129), 1.5 / (129 * 97), 1.0]
+    m = rot(kb, sw, sh, 30.0)
+    om = oracle.BILINEAR if mode == "Bilinear" else oracle.NEAREST
+    kb._lib.set_knob("warp.path", 4)
+    try:
+        dst = kb.Image.zeros_cuda(kb.ImageSize(sw, sh), 3, torch.float32, dev)
+        kb.imgproc.warp_perspective(kb.Image(cu(src, dev)), dst, h, kb.InterpolationMode[mode])
+        assert last_kernel(kb) == "warp_gather64_kernel"
+        assert_f32_equal(dst.numpy(), oracle.warp_perspective_f32(src, h, sw, sh, om), "gather64 perspective")
+        kb.imgproc.warp_affine(kb.Image(cu(src, dev)), dst, m, kb.InterpolationMode[mode])
+        assert last_kernel(kb) == "warp_gather64_kernel"
+        assert_f32_equal(dst.numpy(), oracle.warp_affine_f32(src, m, sw, sh, om), "gather64 affine")
+    finally:
+        kb._lib.set_knob("warp.path", 0)
