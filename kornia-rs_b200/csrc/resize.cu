@@ -8,11 +8,9 @@
 // unfused multiply-add, weights are formed first and the four terms summed left to right.  This
 // file is compiled with -fmad=false, so plain `*` and `+` already round twice.
 //
-// B200 design (round 1): thread-per-destination-pixel gather with batch as grid.z; source rows are
-// read through the read-only path (the 2x2 taps of neighbouring threads share sectors, L1 absorbs
-// the reuse), destination rows are written fully coalesced (a warp covers 32 consecutive pixels =
-// 384 contiguous bytes).  The TMA row-span staged variant for the u8→f32 CHW headline path lives in
-// resize_fused.cu.
+// The f32 bilinear hot kernel is the row-streaming one in resize_rows.cu (TMA row ring, shared-memory taps, STG.128
+// rows); the kernels here are its gather fallback (unaligned rows, nearest, generic channel counts) and the u8 family.
+// The TMA row-span staged variant for the u8→f32 CHW headline path lives in resize_fused.cu.
 #include "kb200_common.cuh"
 
 namespace kb200 {
@@ -32,7 +30,21 @@ static inline void mapping_coeffs(int mapping, uint32_t src_len, uint32_t dst_le
     }
 }
 
-// MODE: 0 nearest, 1 bilinear, 2 bilinear + (v - mean) * inv_std        (cuda/resize.rs:97-235)
+// Gather fallback of the f32 C=3 resize (the row-streaming kernel of resize_rows.cu takes every geometry whose rows are
+// 16-byte aligned; this one takes the rest, and nearest).  MODE: 0 nearest, 1 bilinear, 2 bilinear + (v - mean) * inv_std.
+// Per axis the sampler state is (i0, i1, f) from `axis_taps` — the same expression tree as resize_rows.cu's rr_axis
+// (cuda/resize.rs:113-125: clamp(a*i + b, 0, len-1), trunc, +1 tap clamped) — and a pixel is the weights-first, four-term
+// left-to-right sum of cuda/resize.rs:127-139.  A thread produces one destination pixel; batch = grid.z.
+struct AxisTaps { uint32_t i0, i1; float f; };
+__device__ __forceinline__ AxisTaps axis_taps(uint32_t i, float a, float b, uint32_t len) {
+    const float s = fmaxf(fminf(a * (float)i + b, (float)(len - 1u)), 0.0f);
+    AxisTaps t;
+    t.i0 = (uint32_t)s;
+    t.i1 = min(t.i0 + 1u, len - 1u);
+    t.f = s - (float)t.i0;
+    return t;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) resize_f32_c3_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                             uint32_t sw, uint32_t sh, uint32_t dw, uint32_t dh, AxisMap m,
@@ -43,33 +55,26 @@ __global__ void __launch_bounds__(256) resize_f32_c3_kernel(const float* __restr
     if (x >= dw || y >= dh) return;
     const float* s = src + (size_t)blockIdx.z * sw * sh * 3;
     float* d = dst + ((size_t)blockIdx.z * dw * dh + (size_t)y * dw + x) * 3;
-    if (MODE == 0) {
+    if (MODE == 0) {   // cuda/resize.rs:146-175: (a*i + b) + 0.5, truncated, clamped to the last index
         const uint32_t xi = min((uint32_t)((m.ax * (float)x + m.bx) + 0.5f), sw - 1u);
         const uint32_t yi = min((uint32_t)((m.ay * (float)y + m.by) + 0.5f), sh - 1u);
         const float* p = s + ((size_t)yi * sw + xi) * 3;
         d[0] = __ldg(p); d[1] = __ldg(p + 1); d[2] = __ldg(p + 2);
         return;
     }
-    const float sx = fmaxf(fminf(m.ax * (float)x + m.bx, (float)(sw - 1u)), 0.0f);
-    const float sy = fmaxf(fminf(m.ay * (float)y + m.by, (float)(sh - 1u)), 0.0f);
-    const uint32_t x0 = (uint32_t)sx, y0 = (uint32_t)sy;
-    const uint32_t x1 = min(x0 + 1u, sw - 1u), y1 = min(y0 + 1u, sh - 1u);
-    const float fx = sx - (float)x0, fy = sy - (float)y0;
-    const float w00 = (1.0f - fy) * (1.0f - fx);
-    const float w10 = (1.0f - fy) * fx;
-    const float w01 = fy * (1.0f - fx);
-    const float w11 = fy * fx;
-    const float* p00 = s + ((size_t)y0 * sw + x0) * 3;
-    const float* p10 = s + ((size_t)y0 * sw + x1) * 3;
-    const float* p01 = s + ((size_t)y1 * sw + x0) * 3;
-    const float* p11 = s + ((size_t)y1 * sw + x1) * 3;
-    float c[3];
+    const AxisTaps tx = axis_taps(x, m.ax, m.bx, sw), ty = axis_taps(y, m.ay, m.by, sh);
+    const float gy = 1.0f - ty.f, gx = 1.0f - tx.f;
+    const float w[4] = {gy * gx, gy * tx.f, ty.f * gx, ty.f * tx.f};          // taps (x0,y0) (x1,y0) (x0,y1) (x1,y1)
+    const float* r0 = s + (size_t)ty.i0 * sw * 3;
+    const float* r1 = s + (size_t)ty.i1 * sw * 3;
+    const float* tap[4] = {r0 + tx.i0 * 3u, r0 + tx.i1 * 3u, r1 + tx.i0 * 3u, r1 + tx.i1 * 3u};
+    const float mean[3] = {mean0, mean1, mean2}, inv[3] = {is0, is1, is2};
 #pragma unroll
-    for (int k = 0; k < 3; ++k) c[k] = w00 * __ldg(p00 + k) + w10 * __ldg(p10 + k) + w01 * __ldg(p01 + k) + w11 * __ldg(p11 + k);
-    if (MODE == 2) {
-        c[0] = (c[0] - mean0) * is0; c[1] = (c[1] - mean1) * is1; c[2] = (c[2] - mean2) * is2;
+    for (int k = 0; k < 3; ++k) {
+        float c = w[0] * __ldg(tap[0] + k) + w[1] * __ldg(tap[1] + k) + w[2] * __ldg(tap[2] + k) + w[3] * __ldg(tap[3] + k);
+        if (MODE == 2) c = (c - mean[k]) * inv[k];
+        d[k] = c;
     }
-    d[0] = c[0]; d[1] = c[1]; d[2] = c[2];
 }
 
 // Generic channel count, CPU `resize<C>` semantics (val00 replicate, round() for nearest).
