@@ -3,11 +3,11 @@
 
 The reference (kornia-rs) ships its GPU kernels as CUDA-C source strings inside Rust files and JIT-compiles them with
 NVRTC for `compute_XY` with `--fmad=false` (crates/kornia-tensor/src/cuda.rs:675-718).  This script reads those strings
-from /root/reference *where they lie*, writes each NVRTC translation unit verbatim to `baseline/_ref/kernels/<unit>.cu`,
-compiles it exactly like the reference does (NVRTC, `--gpu-architecture=compute_100 --fmad=false`, nothing else) to
-`baseline/_ref/ptx/<unit>.ptx`, and records a manifest.  `baseline/_ref/` is git-ignored (reference sources are never
-committed) but travels to the GPU box with the snapshot, where `baseline/ref_gpu.py` loads the PTX through the driver
-API and launches it with the reference's launch geometry.  Test / measurement infrastructure only: nothing here is
+from /root/reference *where they lie*, compiles each NVRTC translation unit IN MEMORY exactly like the reference does
+(NVRTC, `--gpu-architecture=compute_100 --fmad=false`, nothing else) to `baseline/_ref/ptx/<unit>.ptx`, and records a
+manifest (unit -> reference file:line, kernel names).  Only the compiled PTX is kept — the source text is never written
+into the repository tree; `baseline/_ref/` is git-ignored and travels to the GPU box with the snapshot like a built .so,
+where `baseline/ref_gpu.py` loads the PTX through the driver API and launches it with the reference's launch geometry.  Test / measurement infrastructure only: nothing here is
 linked into, imported by or shipped with the product library.
 
 Run by `__graft_entry__.build()` whenever /root/reference is present.
@@ -170,13 +170,12 @@ def main() -> int:
     if not os.path.isdir(REF):
         print(f"[ref-kernels] {REF} not present: keeping whatever baseline/_ref already holds")
         return 0
-    os.makedirs(os.path.join(OUT, "kernels"), exist_ok=True)
+    import shutil
+
+    shutil.rmtree(os.path.join(OUT, "kernels"), ignore_errors=True)     # source text is never kept: only the compiled PTX
     os.makedirs(os.path.join(OUT, "ptx"), exist_ok=True)
     manifest = {}
     for u in units():
-        cu = os.path.join(OUT, "kernels", u["unit"] + ".cu")
-        with open(cu, "w") as f:
-            f.write(u["src"])
         ptx = nvrtc_ptx(u["src"], u["unit"])
         with open(os.path.join(OUT, "ptx", u["unit"] + ".ptx"), "wb") as f:
             f.write(ptx)
