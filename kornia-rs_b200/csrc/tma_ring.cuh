@@ -64,6 +64,36 @@ __device__ __forceinline__ void load_1d(void* smem_dst, const void* gmem_src, ui
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 1-D bulk copy shared::cta -> global through the TMA engine (SASS UBLKCP with the S2G flavour): whole, byte-exact sectors
+// reach L2 however the threads filled the shared buffer.  bytes % 16 == 0, both addresses 16-B aligned.  The writers make
+// their shared-memory stores visible to the async proxy first (fence_proxy_async, then a warp / block sync), one thread
+// issues the copy, commits the group and — before the buffer is reused or the CTA exits — waits until it has been READ.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+// one lane of `mask` (the same lane for every call with that mask): lets the compiler issue the uniform-datapath TMA
+// instructions straight-line instead of a per-lane waterfall loop
+__device__ __forceinline__ bool elect_one(unsigned mask) {
+    uint32_t p;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, %1;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(p) : "r"(mask));
+    return p != 0;
+}
+__device__ __forceinline__ void store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// A warp has filled `bytes` (a multiple of 16) of its 16-byte aligned shared buffer with results: one TMA copy writes them
+// to global memory as whole sectors.  Used by the kernels whose threads own 3-, 12- or C-byte pixels: their direct stores
+// (lanes a pixel apart, one channel per instruction) send every destination sector to L2 once per channel, a third full.
+__device__ __forceinline__ void warp_store_span(void* gmem_dst, const void* smem_src, uint32_t bytes, unsigned mask = 0xFFFFFFFFu) {
+    fence_proxy_async();
+    __syncwarp(mask);
+    if (elect_one(mask)) {
+        store_1d(gmem_dst, smem_src, bytes);
+        store_commit();
+        store_wait_read<0>();       // before the CTA (and its shared memory) goes away
+    }
+}
 // named barrier among `count` threads of the CTA (consumer warps only; the producer warp never joins)
 __device__ __forceinline__ void named_barrier(uint32_t id, uint32_t count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");

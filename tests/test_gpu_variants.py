@@ -356,6 +356,107 @@ def test_warp_perspective_stream(kb, oracle, dev, name, h, mode, size):
     assert_f32_equal(dst.numpy(), want, f"stream perspective {name} {mode} {size}")
 
 
+# ── warp_bilinear_lean_kernel (round 2, second pass): interior fast path + per-pixel general path ──────────
+def _scaled(h, k):
+    return [v * k for v in h]
+
+
+LEAN_H = STREAM_H + [
+    ("cfg5", H_CFG5),
+    ("negative-denominator", _scaled(STREAM_H[0][1], -1.0)),       # the same map; every w of the inverse is negative
+    ("denominator-1e3", _scaled(STREAM_H[0][1], 1.0e-3)),          # inverse scaled by 1e3: w ~ 1e3, numerators ~ 1e6
+    ("denominator-3e-4", _scaled(STREAM_H[0][1], 3.0e3)),          # w ~ 3e-4: just inside the host-proved window
+    ("denominator-outside-window", _scaled(STREAM_H[0][1], 3.0e4)),    # w ~ 3e-5: the host refuses the fast path
+    ("w-crosses-zero", [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 3.0e-3, 0.0, 1.0]),   # inverse denominator changes sign inside the image
+    ("origin-on-a-pixel", [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 1.0e-4, 2.0e-4, 1.0]),   # numerators exactly 0 along the first row / column
+]
+
+
+@pytest.mark.parametrize("name,h", LEAN_H)
+@pytest.mark.parametrize("size", [(640, 360), (389, 211), (97, 61)])
+def test_warp_perspective_lean(kb, oracle, dev, name, h, size):
+    """Every dispatch of the bilinear gather: the lean kernel with the fast path allowed (knob a = 0), with the general path
+    forced (a = 4) and the round-2 x4 kernel (a = 3) must all give the oracle's bits.  Sizes: multiples of 32 and not (partial
+    warps vote with the live-lane mask; a last block row with one or two rows of a pair missing)."""
+    sw, sh = size
+    n = 2
+    src = oracle.pattern_f32(n * sw * sh * 3).reshape(n, sh, sw, 3)
+    want = np.stack([oracle.warp_perspective_f32(src[i], h, sw, sh, oracle.BILINEAR) for i in range(n)])
+    t = kb.Image(cu(src, dev))
+    stg = "" if sw % 4 == 0 else "/stg"       # TMA tile stores need 16-byte aligned destination rows
+    lean, gen = "warp_bilinear_lean_kernel", "warp_bilinear_lean_kernel/general"
+    # knob a: 0 default, 4 general path only, 5 STG stores, 3 the round-2 x4 kernel
+    for a, d, kernels in ((0, 0, (lean + stg, gen + stg)), (4, 0, (gen + stg,)), (5, 0, (lean + "/stg", gen + "/stg")), (3, 0, ("warp_bilinear_x4_kernel",))):
+        dst = kb.Image.from_size_val(kb.ImageSize(sw, sh), 9.0, 3, torch.float32, dev, batch=n)
+        kb._lib.set_knob("a", a)
+        kb._lib.set_knob("d", d)
+        kb._lib.set_knob("warp.path", 1)
+        try:
+            kb.imgproc.warp_perspective(t, dst, h, kb.InterpolationMode.Bilinear)
+            k = last_kernel(kb)
+        finally:
+            kb._lib.set_knob("a", 0)
+            kb._lib.set_knob("d", 0)
+            kb._lib.set_knob("warp.path", 0)
+        assert k in kernels, k
+        if a == 0 and (name == "denominator-outside-window" or (name == "w-crosses-zero" and sw > 340)):   # w = 1 - 0.003 x
+            assert k == gen + stg, k
+        if a == 0 and name in ("cfg5", "cfg5-like", "negative-denominator", "denominator-1e3", "denominator-3e-4", "identity"):
+            assert k == lean + stg, k
+        assert_f32_equal(dst.numpy(), want, f"lean perspective {name} {size} a={a} d={d} ({k})")
+
+
+@pytest.mark.parametrize("angle,scale", [(0.0, 1.0), (2.0, 1.0), (-3.5, 0.9), (8.0, 1.2), (90.0, 1.0), (180.0, 0.7)])
+@pytest.mark.parametrize("dsize", [(480, 260), (333, 201)])
+def test_warp_affine_lean(kb, oracle, dev, angle, scale, dsize):
+    """Affine maps through the lean gather kernel (path knob 1 keeps rotations off the tiled kernel); 90 degrees is the
+    degenerate-axis case (|m0| < 1e-6: validity judged on the row constant) which must take the general path."""
+    sw, sh = 512, 300
+    dw, dh = dsize
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3)
+    m = rot(kb, sw, sh, angle, scale)
+    want = oracle.warp_affine_f32(src, m, dw, dh, oracle.BILINEAR)
+    t = kb.Image(cu(src, dev))
+    for a, d in ((0, 0), (4, 0), (5, 0), (3, 0)):
+        dst = kb.Image.from_size_val(kb.ImageSize(dw, dh), 9.0, 3, torch.float32, dev)
+        kb._lib.set_knob("a", a)
+        kb._lib.set_knob("d", d)
+        kb._lib.set_knob("warp.path", 1)
+        try:
+            kb.imgproc.warp_affine(t, dst, m, kb.InterpolationMode.Bilinear)
+            k = last_kernel(kb)
+        finally:
+            kb._lib.set_knob("a", 0)
+            kb._lib.set_knob("d", 0)
+            kb._lib.set_knob("warp.path", 0)
+        if a == 0:
+            stg = "" if dw % 4 == 0 else "/stg"
+            # cos 90 / sin 180 are ~1e-8 in f32, not 0: degenerate axes (|m| < 1e-6, judged on the row constant) -> general path;
+            # sin 0 is exactly 0: coordinate == row constant, the fast path stays
+            assert k == ("warp_bilinear_lean_kernel/general" if angle in (90.0, 180.0) else "warp_bilinear_lean_kernel") + stg, k
+        assert_f32_equal(dst.numpy(), want, f"lean affine {angle} x{scale} {dsize} a={a} d={d} ({k})")
+
+
+def test_warp_lean_nonfinite_and_degenerate_matrices(kb, oracle, dev):
+    """A source holding inf / NaN (0 * inf must stay NaN: all four taps are always read) and a homography whose inverse has a
+    NaN-producing row: the result must match the oracle element for element (NaN == NaN here)."""
+    sw, sh = 160, 96
+    src = oracle.pattern_f32(sw * sh * 3).reshape(sh, sw, 3).copy()
+    src[10, 20, 0] = np.inf; src[11, 21, 1] = -np.inf; src[40, 50, 2] = np.nan
+    h = [1.01, 0.02, -3.0, -0.02, 1.02, 2.0, 1.0e-5, 5.0e-6, 1.0]
+    dst = kb.Image.from_size_val(kb.ImageSize(sw, sh), 9.0, 3, torch.float32, dev)
+    kb._lib.set_knob("warp.path", 1)
+    try:
+        kb.imgproc.warp_perspective(kb.Image(cu(src, dev)), dst, h, kb.InterpolationMode.Bilinear)
+        assert last_kernel(kb) == "warp_bilinear_lean_kernel"
+    finally:
+        kb._lib.set_knob("warp.path", 0)
+    got, want = dst.numpy(), oracle.warp_perspective_f32(src, h, sw, sh, oracle.BILINEAR)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    fin = ~np.isnan(want)
+    assert np.array_equal(got[fin].view(np.uint32), want[fin].view(np.uint32))
+
+
 @pytest.mark.parametrize("angle,scale", [(0.0, 1.0), (2.0, 1.0), (-3.5, 0.9), (8.0, 1.2), (30.0, 1.0)])
 @pytest.mark.parametrize("mode", ["Bilinear", "Nearest"])
 def test_warp_affine_stream(kb, oracle, dev, angle, scale, mode):
@@ -655,3 +756,4 @@ def test_warp_gather64_fallback(kb, oracle, dev, mode):
         assert_f32_equal(dst.numpy(), oracle.warp_affine_f32(src, m, sw, sh, om), "gather64 affine")
     finally:
         kb._lib.set_knob("warp.path", 0)
+

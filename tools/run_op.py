@@ -55,6 +55,15 @@ elif op == "rgb_nv12":
     raw = torch.randint(0, 256, (64, 1920 * 1080 * 3 // 2), dtype=torch.uint8, device=dev, generator=g)
     rgb = kb.Image.zeros_cuda(kb.ImageSize(1920, 1080), 3, torch.uint8, dev, batch=64)
     fn = lambda: kb.imgproc.rgb_from_nv12(raw, rgb)
+elif op == "blur_u8":
+    u8 = kb.Image(torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g))
+    o8 = kb.Image.zeros_cuda(kb.ImageSize(3840, 2160), 3, torch.uint8, dev, batch=8)
+    fn = lambda: kb.imgproc.gaussian_blur_u8(u8, o8, (5, 5), (1.5, 1.5))
+elif op == "warp_u8":
+    u8 = kb.Image(torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g))
+    o8 = kb.Image.zeros_cuda(kb.ImageSize(3840, 2160), 3, torch.uint8, dev, batch=8)
+    H = [1.02, 0.03, -40.0, -0.03, 1.01, 25.0, 2.0e-6, 1.2e-6, 1.0]
+    fn = lambda: kb.imgproc.warp_perspective_u8(u8, o8, H)
 elif op == "std_mean":
     u8 = kb.Image(torch.randint(0, 256, (32, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g))
     fn = lambda: kb.imgproc.std_mean_sums(u8)
