@@ -251,9 +251,33 @@ __device__ __forceinline__ uint32_t u8s_q8_lanes(const uint32_t (&x)[7], const u
     for (int t = 0; t < 7; ++t) {
         if (t >= n) break;
         ae += (x[t] & 0x00FF00FFu) * k[t];
-        ao += ((x[t] >> 8) & 0x00FF00FFu) * k[t];
+        ao += __byte_perm(x[t], 0u, 0x4341u) * k[t];          // bytes 1 and 3 into the two 16-bit lanes: one PRMT (the kernel is ALU-pipe bound)
     }
-    return ((ae >> 8) & 0x00FF00FFu) | (ao & 0xFF00FF00u);
+    return __byte_perm(ae, ao, 0x7351u);                      // high byte of each lane, even / odd interleaved: ((ae >> 8) & 0x00FF00FF) | (ao & 0xFF00FF00)
+}
+
+// The horizontal taps of a word whose support crosses the left / right image border (replicate border in x: clamped pixel
+// index per byte).  Only the first and last couple of threads of a row take it, but inlined and unrolled into every one of
+// the K x NV copies of the row step it made the kernel 127 registers (3 CTAs per SM) and large enough to miss the instruction
+// cache (ncu: no-instruction stalls, instruction-cache requests 79 % of peak) — so: one rolled, out-of-line copy.
+// Replicate border in x without an edge path: after a row has landed, the warp that owns the first word of the row writes
+// the 16 halo bytes left of it (bytes at row position p < 0 are channel p mod C of pixel 0 — a byte permutation of the row's
+// first word), and the warp that owns the last word writes the 16 bytes right of it (channel q mod C of the last pixel — a
+// permutation of the last word; rows are a multiple of 16 bytes, so the four words around the row end sit in one warp).  Both
+// regions are outside what the TMA copy writes.  Every thread then takes the same word-granular taps.  (Round 2 had a byte-wise
+// clamped path for the threads at the border: inlined it cost 127 registers and an instruction-cache-missing kernel, out of
+// line it stalled the whole CTA behind one warp.)
+template <int C>
+__host__ __device__ constexpr uint32_t u8s_sel_left(int j) {          // word j of the halo: row positions -16 + 4j .. + 3
+    uint32_t sel = 0;
+    for (int b = 0; b < 4; ++b) { const int p = -16 + 4 * j + b; sel |= (uint32_t)(((p % C) + C) % C) << (4 * b); }
+    return sel;
+}
+template <int C>
+__host__ __device__ constexpr uint32_t u8s_sel_right(int j) {         // word j past the row end: row positions rowb + 4j .. + 3
+    uint32_t sel = 0;
+    for (int b = 0; b < 4; ++b) { const int q = 4 * j + b; sel |= (uint32_t)(4 - C + (q % C)) << (4 * b); }
+    return sel;
 }
 
 template <int C, int K, int NV>
@@ -300,7 +324,7 @@ __global__ void __launch_bounds__(U8S_THREADS) blur_u8_stream_kernel(const uint8
     uint32_t kx[7], ky[7];
 #pragma unroll
     for (int k = 0; k < 7; ++k) { kx[k] = k < K ? T.kx[k] : 0u; ky[k] = k < K ? T.ky[k] : 0u; }
-    const bool binomial = T.binomial != 0;
+    const bool binomial = K == 3 && T.binomial != 0;
     const bool lane0 = (tid & 31u) == 0;
     const int cols = (int)(P.rowb / C);
     for (uint32_t u = blockIdx.x; u < P.nunits; u += gridDim.x) {
@@ -310,75 +334,89 @@ __global__ void __launch_bounds__(U8S_THREADS) blur_u8_stream_kernel(const uint8
         const int y_first = (int)(chunk * P.rows_per_chunk), y_end = min(y_first + (int)P.rows_per_chunk, (int)P.rows);
         uint8_t* out = dst + (size_t)img * img_bytes + (size_t)y_first * P.rowb;
         int B[NV];            // first global byte (within the row) of this thread's word column v
-        bool act[NV], edge[NV];
+        bool act[NV];
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
             B[v] = e0 + 4 * ((int)tid + v * U8S_CT);
             act[v] = B[v] < (int)P.rowb;
-            edge[v] = B[v] - HX * C < 0 || B[v] + 3 + HX * C >= (int)P.rowb;     // taps cross the left / right border: clamp per byte
         }
+        const int last_word = ((int)P.rowb - e0) / 4 - 1;                                   // strip-relative word index of the row's last word
+        const bool lpatch = e0 == 0 && tid < 32u;                                          // this warp owns the row's first word
+        const bool rpatch = last_word < U8S_CT * NV && ((last_word % U8S_CT) >> 5) == (int)(tid >> 5);   // ... its last word (warp-uniform)
+        // K-deep register window of H-pass results, oldest first.  The row loop is NOT unrolled: rotating the window costs
+        // (K-1)*NV register moves per row, whereas K unrolled copies of the row step made the kernel ~40 KB of code that
+        // missed the instruction cache on every lap (ncu: no-instruction stalls, icache requests 45-79 % of peak).
         uint32_t win[K][NV];
-        int iy = y_first - HY;
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) win[s][v] = 0u;
         const int iy_end = y_end + HY;
-        while (iy < iy_end) {
+#pragma unroll 1
+        for (int iy = y_first - HY; iy < iy_end; ++iy) {
+            tma::mbar_wait(&full_bar[stage], phase);
+            uint8_t* slot = u8s_smem + (size_t)stage * P.slot_bytes;                // slot byte j = row byte e0 - 16 + j
+            if (lpatch) {
+                if (tid == 0) {
+                    uint32_t* sw = reinterpret_cast<uint32_t*>(slot);
+                    const uint32_t w = sw[U8S_HALO / 4];
 #pragma unroll
-            for (int s = 0; s < K; ++s) {          // unrolled: window slot indices are compile-time
-                if (iy >= iy_end) break;
-                tma::mbar_wait(&full_bar[stage], phase);
-                const uint8_t* slot = u8s_smem + (size_t)stage * P.slot_bytes;          // slot byte j = row byte e0 - 16 + j
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    uint32_t hres = 0;
-                    if (act[v]) {
-                        uint32_t x[7];
-                        if (!edge[v]) {
-                            // tap t of output bytes B..B+3 starts at row byte B + (t - HX)*C: word index and shift are
-                            // compile-time relative to this thread's word
-                            const uint32_t* wp = reinterpret_cast<const uint32_t*>(slot) + (U8S_HALO / 4) + tid + v * U8S_CT;
-#pragma unroll
-                            for (int t = 0; t < 7; ++t) {
-                                if (t >= K) break;
-                                constexpr int dummy = 0; (void)dummy;
-                                const int off = (t - HX) * C;                           // byte offset, may be negative
-                                const int wi = (off >= 0) ? (off >> 2) : -((-off + 3) >> 2);
-                                const int sh = off - 4 * wi;                            // 0..3
-                                x[t] = sh == 0 ? wp[wi] : __funnelshift_r(wp[wi], wp[wi + 1], 8 * sh);
-                            }
-                        } else {
-#pragma unroll
-                            for (int t = 0; t < 7; ++t) {
-                                if (t >= K) break;
-                                uint32_t w = 0;
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int gb = B[v] + j, px = gb / C, ch = gb - px * C;
-                                    const int sx = min(max(px + t - HX, 0), cols - 1);    // replicate border in x
-                                    w |= (uint32_t)slot[sx * C + ch - (e0 - U8S_HALO)] << (8 * j);
-                                }
-                                x[t] = w;
-                            }
-                        }
-                        hres = binomial ? avg4_round_up(avg4_round_up(x[0], x[1]), avg4_round_up(x[1], x[2])) : u8s_q8_lanes(x, kx, K);
-                    }
-                    win[s][v] = hres;
+                    for (int j = 0; j < 4; ++j) sw[j] = __byte_perm(w, 0u, u8s_sel_left<C>(j));
+                    tma::fence_proxy_async();      // a later TMA copy (another strip's row) may overwrite these bytes
                 }
                 __syncwarp();
-                if (lane0) tma::mbar_arrive(&empty_bar[stage]);
-                if (++stage == nst) { stage = 0; phase ^= 1u; }
-                // output row r = iy - HY is complete: its window is slots s+1 .. s+K (mod K), oldest first
-                if (iy - HY >= y_first) {
+            }
+            if (rpatch) {
+                if ((int)tid == last_word % U8S_CT) {
+                    uint32_t* sw = reinterpret_cast<uint32_t*>(slot) + U8S_HALO / 4 + last_word;
+                    const uint32_t w = sw[0];
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        if (!act[v]) continue;
-                        uint32_t y[7];
-#pragma unroll
-                        for (int t = 0; t < 7; ++t) y[t] = t < K ? win[(s + 1 + t) % K][v] : 0u;
-                        const uint32_t o = binomial ? avg4_round_up(avg4_round_up(y[0], y[1]), avg4_round_up(y[1], y[2])) : u8s_q8_lanes(y, ky, K);
-                        *reinterpret_cast<uint32_t*>(out + B[v]) = o;
-                    }
-                    out += P.rowb;
+                    for (int j = 0; j < 4; ++j) sw[1 + j] = __byte_perm(w, 0u, u8s_sel_right<C>(j));
+                    tma::fence_proxy_async();
                 }
-                ++iy;
+                __syncwarp();
+            }
+            uint32_t hres[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                hres[v] = 0;
+                if (act[v]) {
+                    uint32_t x[7];
+                    // tap t of output bytes B..B+3 starts at row byte B + (t - HX)*C: word index and shift are compile-time
+                    // relative to this thread's word
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(slot) + (U8S_HALO / 4) + tid + v * U8S_CT;
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) {
+                        if (t >= K) break;
+                        const int off = (t - HX) * C;                           // byte offset, may be negative
+                        const int wi = (off >= 0) ? (off >> 2) : -((-off + 3) >> 2);
+                        const int sh = off - 4 * wi;                            // 0..3
+                        x[t] = sh == 0 ? wp[wi] : __funnelshift_r(wp[wi], wp[wi + 1], 8 * sh);
+                    }
+                    hres[v] = binomial ? avg4_round_up(avg4_round_up(x[0], x[1]), avg4_round_up(x[1], x[2])) : u8s_q8_lanes(x, kx, K);
+                }
+            }
+            __syncwarp();
+            if (lane0) tma::mbar_arrive(&empty_bar[stage]);
+            if (++stage == nst) { stage = 0; phase ^= 1u; }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+#pragma unroll
+                for (int s = 0; s + 1 < K; ++s) win[s][v] = win[s + 1][v];
+                win[K - 1][v] = hres[v];
+            }
+            // output row r = iy - HY is complete: its window is win[0..K-1]
+            if (iy - HY >= y_first) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    if (!act[v]) continue;
+                    uint32_t y[7];
+#pragma unroll
+                    for (int t = 0; t < 7; ++t) y[t] = t < K ? win[t][v] : 0u;
+                    const uint32_t o = binomial ? avg4_round_up(avg4_round_up(y[0], y[1]), avg4_round_up(y[1], y[2])) : u8s_q8_lanes(y, ky, K);
+                    *reinterpret_cast<uint32_t*>(out + B[v]) = o;
+                }
+                out += P.rowb;
             }
         }
     }

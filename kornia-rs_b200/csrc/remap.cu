@@ -42,13 +42,41 @@ __global__ void __launch_bounds__(256) remap_f32_c3_kernel(const float* __restri
 }
 
 template <int C, bool BILINEAR>
+__device__ __forceinline__ void remap_u8_general_pixel(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, float xf, float yf, int sw, int sh, bool words);
+
+constexpr uint32_t REMAP_U8_PX = 4;      // pixels per thread (i, i + 256, ...): the per-thread set-up is a third of a one-pixel thread
+
+template <int C, bool BILINEAR>
 __global__ void __launch_bounds__(256) remap_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const float* __restrict__ map_x,
-                                                       const float* __restrict__ map_y, int sw, int sh, uint32_t npx, bool words) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npx) return;
+                                                       const float* __restrict__ map_y, int sw, int sh, uint32_t npx, bool words, bool aligned) {
     const uint8_t* s = src + (size_t)blockIdx.y * sw * sh * C;
-    uint8_t* d = dst + ((size_t)blockIdx.y * npx + i) * C;
-    const float xf = __ldg(map_x + i), yf = __ldg(map_y + i);
+    uint8_t* dimg = dst + (size_t)blockIdx.y * npx * C;
+    const bool fast_ok = BILINEAR && C == 3 && aligned && sw >= 4 && sh >= 3;
+    const float xlim = (float)(sw - 1), ylim = (float)(sh - 2);
+#pragma unroll
+    for (uint32_t j = 0; j < REMAP_U8_PX; ++j) {
+        const uint32_t ir = (blockIdx.x * REMAP_U8_PX + j) * 256u + threadIdx.x;
+        if ((ir & ~31u) >= npx) return;                     // whole warp
+        const bool live = ir < npx;
+        const uint32_t i = live ? ir : npx - 1u;            // lanes past the end recompute the last pixel and store nothing
+        uint8_t* d = dimg + (size_t)i * C;
+        const float xf = __ldg(map_x + i), yf = __ldg(map_y + i);
+        // interior fast path (u8_sampler.cuh): in range (NaN / inf fail), all taps inside, two rows of slack below
+        const bool fastpix = fast_ok && xf >= 0.0f && xf < xlim && yf >= 0.0f && yf < ylim;
+        if (__all_sync(0xFFFFFFFFu, fastpix)) {
+            const uint32_t xi = (uint32_t)xf, yi = (uint32_t)yf;          // floor == trunc here
+            const uint32_t fx = __float2uint_rz((xf - (float)xi) * 1024.0f), fy = __float2uint_rz((yf - (float)yi) * 1024.0f);
+            uint32_t r0, r1, r2;
+            q10_blend_c3_interior(s, (uint32_t)sw * 3u, xi, yi, fx, fy, &r0, &r1, &r2);
+            if (live) { d[0] = (uint8_t)r0; d[1] = (uint8_t)r1; d[2] = (uint8_t)r2; }
+            continue;
+        }
+        if (live) remap_u8_general_pixel<C, BILINEAR>(s, d, xf, yf, sw, sh, words);
+    }
+}
+
+template <int C, bool BILINEAR>
+__device__ __forceinline__ void remap_u8_general_pixel(const uint8_t* __restrict__ s, uint8_t* __restrict__ d, float xf, float yf, int sw, int sh, bool words) {
     bool ok;
     if (BILINEAR) ok = isfinite(xf) && isfinite(yf);
     else ok = xf >= 0.0f && xf < (float)sw && yf >= 0.0f && yf < (float)sh;
@@ -96,6 +124,9 @@ static int remap_check(const void* src, const void* dst, const void* mx, const v
     return KB200_OK;
 }
 
+bool launch_remap_lean(cudaStream_t s, const float* src, float* dst, const float* map_x, const float* map_y, uint32_t sw, uint32_t sh, uint32_t dw,
+                       uint32_t dh, uint32_t batch, int* status);   // warp.cu
+
 }  // namespace kb200
 
 using namespace kb200;
@@ -111,6 +142,12 @@ KB200_API int kb200_remap_f32_c3(kb200_stream_t stream, const float* src, size_t
     const uint32_t npx = dw * dh;
     dim3 grid(div_up(npx, 256u), batch);
     cudaStream_t s = as_stream(stream);
+    if (interp == KB200_INTERP_BILINEAR) {
+        // round 2: the lean bilinear gather of the warps, coordinates from the maps (warp.cu) — four rows per thread, interior
+        // fast path, TMA tile stores: 0.90 -> see profiles/ for the measured time per 16 x 4K
+        int st = KB200_OK;
+        if (launch_remap_lean(s, src, dst, map_x, map_y, sw, sh, dw, dh, batch, &st)) return st;
+    }
     if (interp == KB200_INTERP_BILINEAR) remap_f32_c3_kernel<true><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, sw, sh, npx);
     else remap_f32_c3_kernel<false><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, sw, sh, npx);
     return check_launch("remap_f32_c3_kernel");
@@ -125,15 +162,16 @@ KB200_API int kb200_remap_u8(kb200_stream_t stream, const uint8_t* src, size_t s
     KB200_TRY(check_slice("src", src_len, (size_t)sw * sh * C * batch));
     KB200_TRY(check_slice("dst", dst_len, (size_t)dw * dh * C * batch));
     const uint32_t npx = dw * dh;
-    dim3 grid(div_up(npx, 256u), batch);
+    dim3 grid(div_up(npx, 256u * REMAP_U8_PX), batch);
     cudaStream_t s = as_stream(stream);
     const bool bil = interp == KB200_INTERP_BILINEAR;
     // word taps measured neutral-to-slower for remap (0.751 -> 0.773 ms, 16 x 4K): off unless knob b = 2
-    const bool words = C == 3 && knob(KNOB_B) == 2 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0 && (batch == 1 || ((size_t)sw * sh * 3) % 4 == 0);
+    const bool aligned = C == 3 && knob(KNOB_B) != 1 && (reinterpret_cast<uintptr_t>(src) & 3u) == 0 && (batch == 1 || ((size_t)sw * sh * 3) % 4 == 0);
+    const bool words = aligned && knob(KNOB_B) == 2;
 #define KB200_REMAP_U8(CC)                                                                                         \
     if (C == CC) {                                                                                                 \
-        if (bil) remap_u8_kernel<CC, true><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx, words);     \
-        else remap_u8_kernel<CC, false><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx, words);        \
+        if (bil) remap_u8_kernel<CC, true><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx, words, aligned);     \
+        else remap_u8_kernel<CC, false><<<grid, 256, 0, s>>>(src, dst, map_x, map_y, (int)sw, (int)sh, npx, words, aligned);        \
     }
     KB200_REMAP_U8(1) KB200_REMAP_U8(3) KB200_REMAP_U8(4)
 #undef KB200_REMAP_U8

@@ -757,3 +757,59 @@ def test_warp_gather64_fallback(kb, oracle, dev, mode):
     finally:
         kb._lib.set_knob("warp.path", 0)
 
+
+# ── remap f32 bilinear through the lean gather kernel (round 2, second pass) ──
+@pytest.mark.parametrize("kind", ["identity", "swirl", "random"])
+@pytest.mark.parametrize("dw,dh", [(64, 40), (57, 39), (132, 70)])
+def test_remap_f32_lean(kb, oracle, dev, kind, dw, dh):
+    """remap (bilinear) = the warps' lean gather with coordinates from the maps: fast path / general path / STG stores / the
+    thread-per-pixel kernel (knob a = 0 / 4 / 5 / 6) against the oracle; maps with NaN, inf, out-of-range and last-row/column taps."""
+    from test_gpu_parity import _remap_maps
+    n, sw, sh = 2, 64, 48
+    rng = np.random.default_rng(31)
+    mx, my = _remap_maps(dw, dh, sw, sh, kind, rng)
+    mxi, myi = kb.Image(cu(mx[..., None], dev)), kb.Image(cu(my[..., None], dev))
+    src = np.stack([oracle.pattern_f32(sw * sh * 3, 0x291 + i).reshape(sh, sw, 3) for i in range(n)])
+    want = np.stack([oracle.remap(src[i], mx, my, 1) for i in range(n)])
+    stg = "" if dw % 4 == 0 else "/stg"
+    for a, kernel in ((0, "remap_lean_kernel" + stg), (4, "remap_lean_kernel/general" + stg), (5, "remap_lean_kernel/stg"), (6, "remap_f32_c3_kernel")):
+        kb._lib.set_knob("a", a)
+        try:
+            d = kb.Image(torch.full((n, dh, dw, 3), float("nan"), dtype=torch.float32, device=dev))
+            kb.imgproc.remap(kb.Image(cu(src, dev)), d, mxi, myi, kb.InterpolationMode.Bilinear)
+            assert last_kernel(kb) == kernel, last_kernel(kb)
+        finally:
+            kb._lib.set_knob("a", 0)
+        assert_f32_equal(d.numpy(), want, f"remap lean {kind} {dw}x{dh} a={a}")
+
+
+# ── u8 warps / remap: interior fast path (round 2, second pass) ───────────────
+@pytest.mark.parametrize("sw,sh", [(640, 360), (389, 211), (132, 35)])
+def test_u8_interior_fast_path(kb, oracle, dev, sw, sh):
+    """q10_blend_c3_interior (u8_sampler.cuh) is taken by warps whose 32 pixels are all interior (taps inside, two rows of
+    slack below); everything else goes through the clamped sampler.  Half-pixel shifts, a mild homography and a rotation put
+    the fast/general seam on the last rows and columns; knob b = 1 (no word taps: general sampler everywhere) must agree."""
+    n = 2
+    src = np.stack([oracle.pattern_u8(sw * sh * 3, 0x331 + i).reshape(sh, sw, 3) for i in range(n)])
+    s_img = kb.Image(cu(src, dev))
+    affines = [[1, 0, 0.5, 0, 1, 0.5], [1, 0, -0.5, 0, 1, -1.5], [1.01, 0.02, -3.0, -0.015, 0.99, 2.5], [0.5, 0, 0, 0, 0.5, 0]]
+    persps = [[1, 0, 0.5, 0, 1, 0.5, 0, 0, 1], [1.02, 0.03, -5.0, -0.03, 1.01, 2.0, 0.00005, 0.00003, 1.0], [-1.0, 0, sw - 1.5, 0, -1.0, sh - 1.5, 0, 0, -1.0]]
+    y, x = np.meshgrid(np.arange(sh, dtype=np.float32), np.arange(sw, dtype=np.float32), indexing="ij")
+    maps = [(x + np.float32(0.5), y + np.float32(0.5)), (x * np.float32(0.999) + np.float32(0.25), y * np.float32(1.001) - np.float32(0.125))]
+    for b in (0, 1):
+        kb._lib.set_knob("b", b)
+        try:
+            for m in affines:
+                d = kb.Image(torch.full((n, sh, sw, 3), 0xCD, dtype=torch.uint8, device=dev))
+                kb.imgproc.warp_affine_u8(s_img, d, m)
+                np.testing.assert_array_equal(d.numpy(), np.stack([oracle.warp_affine_u8(src[i], sw, sh, m) for i in range(n)]), err_msg=f"affine {m} b={b}")
+            for hm in persps:
+                d = kb.Image(torch.full((n, sh, sw, 3), 0xCD, dtype=torch.uint8, device=dev))
+                kb.imgproc.warp_perspective_u8(s_img, d, hm)
+                np.testing.assert_array_equal(d.numpy(), np.stack([oracle.warp_perspective_u8(src[i], sw, sh, hm) for i in range(n)]), err_msg=f"perspective {hm} b={b}")
+            for mx, my in maps:
+                d = kb.Image(torch.full((n, sh, sw, 3), 0xCD, dtype=torch.uint8, device=dev))
+                kb.imgproc.remap_u8(s_img, d, kb.Image(cu(mx[..., None], dev)), kb.Image(cu(my[..., None], dev)), kb.InterpolationMode.Bilinear)
+                np.testing.assert_array_equal(d.numpy(), np.stack([oracle.remap(src[i], mx, my, 1) for i in range(n)]), err_msg=f"remap b={b}")
+        finally:
+            kb._lib.set_knob("b", 0)
