@@ -40,11 +40,11 @@ if "warp" in what:
     yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
     r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / float(w * w)
     mx = kb.Image((w / 2 + (xx - w / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous()); my = kb.Image((h / 2 + (yy - h / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())
-    for a in (0, 5, 6):       # lean + TMA tile stores, lean + STG, thread-per-pixel kernel
-        kb._lib.set_knob("a", a)
+    for a, pf in ((0, 0), (0, -1), (0, 64), (0, 256), (5, 0), (6, 0)):       # lean + TMA tile stores (map-driven L2 prefetch on / off), lean + STG, thread-per-pixel kernel
+        kb._lib.set_knob("a", a); kb._lib.set_knob("warp.pf", pf)
         ms = timeit(lambda: kb.imgproc.remap(s, d_, mx, my, kb.InterpolationMode.Bilinear))
-        print(f"remap_f32 a={a} {kb._lib.last_kernel():28s} {ms:.4f} ms frac {n*w*h*24.5/ms/1e6/PEAK:.3f}", flush=True)
-    kb._lib.set_knob("a", 0)
+        print(f"remap_f32 a={a} pf={pf} {kb._lib.last_kernel():28s} {ms:.4f} ms frac {n*w*h*24.5/ms/1e6/PEAK:.3f}", flush=True)
+    kb._lib.set_knob("a", 0); kb._lib.set_knob("warp.pf", 0)
     del s, d_
 if "u8" in what:
     s8 = kb.Image(torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=dev, generator=g))
