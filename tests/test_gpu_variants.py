@@ -385,8 +385,10 @@ def test_warp_perspective_lean(kb, oracle, dev, name, h, size):
     t = kb.Image(cu(src, dev))
     stg = "" if sw % 4 == 0 else "/stg"       # TMA tile stores need 16-byte aligned destination rows
     lean, gen = "warp_bilinear_lean_kernel", "warp_bilinear_lean_kernel/general"
-    # knob a: 0 default, 4 general path only, 5 STG stores, 3 the round-2 x4 kernel
-    for a, d, kernels in ((0, 0, (lean + stg, gen + stg)), (4, 0, (gen + stg,)), (5, 0, (lean + "/stg", gen + "/stg")), (3, 0, ("warp_bilinear_x4_kernel",))):
+    # knob a: 0 default (one 4-D tensor-map store per warp when dh % 8 == 0, else four 1-D row copies), 7 the 1-D row copies, 4 general
+    # path only, 5 STG stores, 3 the round-2 x4 kernel
+    for a, d, kernels in ((0, 0, (lean + stg, gen + stg)), (7, 0, (lean + stg, gen + stg)), (4, 0, (gen + stg,)), (5, 0, (lean + "/stg", gen + "/stg")),
+                          (3, 0, ("warp_bilinear_x4_kernel",))):
         dst = kb.Image.from_size_val(kb.ImageSize(sw, sh), 9.0, 3, torch.float32, dev, batch=n)
         kb._lib.set_knob("a", a)
         kb._lib.set_knob("d", d)

@@ -23,7 +23,7 @@ if "warp" in what:
     H = [1.02, 0.03, -40.0, -0.03, 1.01, 25.0, 2.0e-6, 1.2e-6, 1.0]
     M = kb.imgproc.get_rotation_matrix2d((w / 2, h / 2), 3.0, 1.0)
     # a: 0 lean + TMA tile stores, 5 lean + STG, 3 round-2 x4
-    for a, pf in ((0, 0), (0, -1), (5, 0), (3, 0)):
+    for a, pf in ((0, 0), (7, 0), (0, -1), (5, 0), (3, 0)):     # 0: one 4-D tensor-map store per warp, 7: four 1-D row copies per warp
         kb._lib.set_knob("a", a); kb._lib.set_knob("warp.pf", pf)
         ms = timeit(lambda: kb.imgproc.warp_perspective(s, d_, H, kb.InterpolationMode.Bilinear))
         print(f"warp_perspective a={a} pf={pf} {kb._lib.last_kernel():36s} {ms:.4f} ms frac {n*w*h*24/ms/1e6/PEAK:.3f}", flush=True)
@@ -40,7 +40,7 @@ if "warp" in what:
     yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
     r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / float(w * w)
     mx = kb.Image((w / 2 + (xx - w / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous()); my = kb.Image((h / 2 + (yy - h / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())
-    for a, pf in ((0, 0), (0, -1), (0, 64), (0, 256), (5, 0), (6, 0)):       # lean + TMA tile stores (map-driven L2 prefetch on / off), lean + STG, thread-per-pixel kernel
+    for a, pf in ((0, 0), (7, 0), (5, 0), (6, 0)):       # lean + tensor-map / 1-D TMA tile stores, lean + STG, thread-per-pixel kernel
         kb._lib.set_knob("a", a); kb._lib.set_knob("warp.pf", pf)
         ms = timeit(lambda: kb.imgproc.remap(s, d_, mx, my, kb.InterpolationMode.Bilinear))
         print(f"remap_f32 a={a} pf={pf} {kb._lib.last_kernel():28s} {ms:.4f} ms frac {n*w*h*24.5/ms/1e6/PEAK:.3f}", flush=True)
