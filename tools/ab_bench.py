@@ -30,13 +30,13 @@ if "warp" in what:
         ms = timeit(lambda: kb.imgproc.warp_affine(s, d_, M, kb.InterpolationMode.Bilinear))
         print(f"warp_affine rot3 a={a} pf={pf} {kb._lib.last_kernel():36s} {ms:.4f} ms frac {n*w*h*24/ms/1e6/PEAK:.3f}", flush=True)
     kb._lib.set_knob("a", 0); kb._lib.set_knob("warp.pf", 0)
-    for ang in (30.0, 10.0, 5.0):
+    for ang in (30.0, 45.0, 10.0):
         M30 = kb.imgproc.get_rotation_matrix2d((w / 2, h / 2), ang, 1.0)
-        for path in (0, 1):       # 0: dispatcher's choice (TMA-tiled for rotations), 1: gather kernels only
-            kb._lib.set_knob("warp.path", path)
+        for c in (0,):
+            kb._lib.set_knob("c", c)
             ms = timeit(lambda: kb.imgproc.warp_affine(s, d_, M30, kb.InterpolationMode.Bilinear))
-            print(f"warp_affine rot{ang:g} path={path} {kb._lib.last_kernel():36s} {ms:.4f} ms frac {n*w*h*24/ms/1e6/PEAK:.3f}", flush=True)
-        kb._lib.set_knob("warp.path", 0)
+            print(f"warp_affine rot{ang:g} box={c} {kb._lib.last_kernel():36s} {ms:.4f} ms frac {n*w*h*24/ms/1e6/PEAK:.3f}", flush=True)
+        kb._lib.set_knob("c", 0)
     yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
     r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / float(w * w)
     mx = kb.Image((w / 2 + (xx - w / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous()); my = kb.Image((h / 2 + (yy - h / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())

@@ -55,6 +55,20 @@ elif op == "rgb_nv12":
     raw = torch.randint(0, 256, (64, 1920 * 1080 * 3 // 2), dtype=torch.uint8, device=dev, generator=g)
     rgb = kb.Image.zeros_cuda(kb.ImageSize(1920, 1080), 3, torch.uint8, dev, batch=64)
     fn = lambda: kb.imgproc.rgb_from_nv12(raw, rgb)
+elif op == "remap":
+    n, w, h = 8, 3840, 2160
+    src = kb.Image(torch.rand((n, h, w, 3), dtype=torch.float32, device=dev, generator=g))
+    dst = kb.Image.zeros_cuda(kb.ImageSize(w, h), 3, torch.float32, dev, batch=n)
+    yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+    r2 = ((xx - w / 2) ** 2 + (yy - h / 2) ** 2) / float(w * w)
+    mx = kb.Image((w / 2 + (xx - w / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous()); my = kb.Image((h / 2 + (yy - h / 2) * (1 + 0.05 * r2)).unsqueeze(-1).contiguous())
+    fn = lambda: kb.imgproc.remap(src, dst, mx, my, kb.InterpolationMode.Bilinear)
+elif op == "fused_general":
+    nb = 16
+    src = torch.randint(0, 256, (nb, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g)
+    p = kb.imgproc.NormalizeParams.from_mean_std(MEAN, STD)
+    dst = torch.empty((nb, 3, 900, 1600), dtype=torch.float32, device=dev)
+    fn = lambda: kb.imgproc.resize_normalize_to_tensor_u8_to_f32_bilinear(src, 1600, 900, p.scale, p.bias, out=dst)
 elif op == "blur_u8":
     u8 = kb.Image(torch.randint(0, 256, (8, 2160, 3840, 3), dtype=torch.uint8, device=dev, generator=g))
     o8 = kb.Image.zeros_cuda(kb.ImageSize(3840, 2160), 3, torch.uint8, dev, batch=8)
