@@ -815,3 +815,61 @@ def test_u8_interior_fast_path(kb, oracle, dev, sw, sh):
                 np.testing.assert_array_equal(d.numpy(), np.stack([oracle.remap(src[i], mx, my, 1) for i in range(n)]), err_msg=f"remap b={b}")
         finally:
             kb._lib.set_knob("b", 0)
+
+
+# ── randomized geometry sweep: every f32 / u8 sampler dispatch against the oracle ─────────────
+def _rand_homography(rng, sw, sh, strength):
+    """Identity + random affine and projective perturbations scaled by `strength` (0 .. 1)."""
+    a = np.eye(3)
+    a[:2, :2] += rng.uniform(-0.35, 0.35, (2, 2)) * strength
+    a[:2, 2] = rng.uniform(-0.2, 0.2, 2) * np.array([sw, sh]) * strength
+    a[2, :2] = rng.uniform(-1.0, 1.0, 2) * strength * 0.6 / max(sw, sh)
+    return [float(v) for v in a.reshape(-1)]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_geometry_sweep(kb, oracle, dev, seed):
+    """Random source / destination sizes (multiples of 32, of 8, of 4, odd) and random maps from near-identity to strongly
+    projective: warp_perspective / warp_affine f32 (bilinear, nearest), their u8 twins and remap (f32, u8) must all equal the
+    oracle bit for bit, whichever kernel the dispatcher picks (lean fast / general path, TMA tile or STG stores, tiled, u8
+    interior sampler)."""
+    rng = np.random.default_rng(1000 + seed)
+    sw, sh = int(rng.choice([64, 96, 131, 200, 256, 333])), int(rng.choice([48, 61, 96, 120, 161]))
+    dw, dh = int(rng.choice([32, 64, 100, 132, 257, 320])), int(rng.choice([24, 40, 56, 75, 128]))
+    n = int(rng.integers(1, 4))
+    strength = float(rng.choice([0.02, 0.1, 0.4, 1.0]))
+    h = _rand_homography(rng, sw, sh, strength)
+    m = h[:6]
+    src = oracle.pattern_f32(n * sw * sh * 3, 0x5000 + seed).reshape(n, sh, sw, 3)
+    t = kb.Image(cu(src, dev))
+    for mode, om in (("Bilinear", oracle.BILINEAR), ("Nearest", oracle.NEAREST)):
+        d = kb.Image.from_size_val(kb.ImageSize(dw, dh), 7.0, 3, torch.float32, dev, batch=n)
+        kb.imgproc.warp_perspective(t, d, h, kb.InterpolationMode[mode])
+        k = last_kernel(kb)
+        assert_f32_equal(d.numpy(), np.stack([oracle.warp_perspective_f32(src[i], h, dw, dh, om) for i in range(n)]), f"seed {seed} perspective {mode} {sw}x{sh}->{dw}x{dh} ({k})")
+        d = kb.Image.from_size_val(kb.ImageSize(dw, dh), 7.0, 3, torch.float32, dev, batch=n)
+        kb.imgproc.warp_affine(t, d, m, kb.InterpolationMode[mode])
+        k = last_kernel(kb)
+        assert_f32_equal(d.numpy(), np.stack([oracle.warp_affine_f32(src[i], m, dw, dh, om) for i in range(n)]), f"seed {seed} affine {mode} {sw}x{sh}->{dw}x{dh} ({k})")
+    src8 = np.stack([oracle.pattern_u8(sw * sh * 3, 0x6000 + seed + i).reshape(sh, sw, 3) for i in range(n)])
+    t8 = kb.Image(cu(src8, dev))
+    d8 = kb.Image(torch.full((n, dh, dw, 3), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.warp_perspective_u8(t8, d8, h)
+    np.testing.assert_array_equal(d8.numpy(), np.stack([oracle.warp_perspective_u8(src8[i], dw, dh, h) for i in range(n)]), err_msg=f"seed {seed} perspective u8")
+    d8 = kb.Image(torch.full((n, dh, dw, 3), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.warp_affine_u8(t8, d8, m)
+    np.testing.assert_array_equal(d8.numpy(), np.stack([oracle.warp_affine_u8(src8[i], dw, dh, m) for i in range(n)]), err_msg=f"seed {seed} affine u8")
+    # remap through the same homography's coordinate field, with a few holes
+    hi = np.linalg.inv(np.array(h, dtype=np.float64).reshape(3, 3))
+    yy, xx = np.meshgrid(np.arange(dh, dtype=np.float64), np.arange(dw, dtype=np.float64), indexing="ij")
+    wq = hi[2, 0] * xx + hi[2, 1] * yy + hi[2, 2]
+    mx = ((hi[0, 0] * xx + hi[0, 1] * yy + hi[0, 2]) / wq).astype(np.float32)
+    my = ((hi[1, 0] * xx + hi[1, 1] * yy + hi[1, 2]) / wq).astype(np.float32)
+    mx[0, 0] = np.nan; my[dh // 2, dw // 2] = np.inf; mx[dh - 1, dw - 1] = sw - 1.0; my[dh - 1, 0] = sh - 1.0
+    mxi, myi = kb.Image(cu(mx[..., None], dev)), kb.Image(cu(my[..., None], dev))
+    d = kb.Image(torch.full((n, dh, dw, 3), float("nan"), dtype=torch.float32, device=dev))
+    kb.imgproc.remap(t, d, mxi, myi, kb.InterpolationMode.Bilinear)
+    assert_f32_equal(d.numpy(), np.stack([oracle.remap(src[i], mx, my, 1) for i in range(n)]), f"seed {seed} remap f32 ({last_kernel(kb)})")
+    d8 = kb.Image(torch.full((n, dh, dw, 3), 0xCD, dtype=torch.uint8, device=dev))
+    kb.imgproc.remap_u8(t8, d8, mxi, myi, kb.InterpolationMode.Bilinear)
+    np.testing.assert_array_equal(d8.numpy(), np.stack([oracle.remap(src8[i], mx, my, 1) for i in range(n)]), err_msg=f"seed {seed} remap u8")
