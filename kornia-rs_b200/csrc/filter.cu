@@ -24,6 +24,7 @@
 #include <type_traits>
 
 #include "kb200_common.cuh"
+#include "pair_math.cuh"
 
 namespace kb200 {
 
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(SS2<NV>::THREADS) sep_filter_stream2_kernel(co
                                 const ss_u64 m = pair_add(pair_mul(gx, gx, pc), pair_mul(gy, gy, pc), pc);   // gx*gx + gy*gy, unfused
                                 float m0, m1;
                                 ss_unpack(m, m0, m1);
-                                o[2 * h] = sqrtf(m0); o[2 * h + 1] = sqrtf(m1);
+                                pair_sqrt_rn(m0, m1, &o[2 * h], &o[2 * h + 1]);     // == sqrtf on both, 12 instructions per pair (pair_math.cuh)
                             } else {
                                 ss_u64 acc = ss_fma2(winA[(s + 1) % KY][v][h], kyp[0], pc.zero);   // == 0 + w*k
 #pragma unroll
