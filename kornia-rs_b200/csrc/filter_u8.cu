@@ -234,10 +234,9 @@ __global__ void __launch_bounds__(256) blur_u8_tile_w_kernel(const uint8_t* __re
 // (image, strip of 128*NV words of a row, chunk of rows); every source row span is copied ONCE global -> shared by the
 // TMA engine (cp.async.bulk, mbarrier ring, producer lane; rows clamped = the reference's replicate border in y); a
 // consumer thread owns NV word columns: the H pass reads the words around its column (compile-time funnel shifts per tap,
-// two 16-bit lanes per register as above), its u8x4 result goes into a K-deep REGISTER window (row loop unrolled K times),
-// and as soon as the window is full the V pass emits one lane-contiguous STG.32 per column.  The u8 intermediate never
-// leaves registers; no __syncthreads in the loop.  Only the few threads whose taps cross the left / right image border
-// take a byte-wise path with clamped column indices (the replicate border in x).
+// two 16-bit lanes per register as above), its result goes — split into even and odd bytes — into a K-deep rotating REGISTER
+// window, and as soon as the window is full the V pass emits one lane-contiguous STG.32 per column.  The u8 intermediate never
+// leaves registers; no __syncthreads in the loop.  The replicate border in x is a 16-byte halo patch in shared memory (below).
 // Needs rows of a multiple of 16 bytes and 16-byte aligned images (TMA); anything else uses the tile kernels.
 static constexpr int U8S_CT = 128, U8S_THREADS = U8S_CT + 32, U8S_MAX_STAGES = 16, U8S_HALO = 16;
 
@@ -245,21 +244,6 @@ struct U8StreamParams {
     uint32_t rowb, rows, strips, chunks, rows_per_chunk, nunits, stages, slot_bytes;
 };
 
-__device__ __forceinline__ uint32_t u8s_q8_lanes(const uint32_t (&x)[7], const uint32_t (&k)[7], int n) {
-    uint32_t ae = 0x00800080u, ao = 0x00800080u;         // + 128 per 16-bit lane
-#pragma unroll
-    for (int t = 0; t < 7; ++t) {
-        if (t >= n) break;
-        ae += (x[t] & 0x00FF00FFu) * k[t];
-        ao += __byte_perm(x[t], 0u, 0x4341u) * k[t];          // bytes 1 and 3 into the two 16-bit lanes: one PRMT (the kernel is ALU-pipe bound)
-    }
-    return __byte_perm(ae, ao, 0x7351u);                      // high byte of each lane, even / odd interleaved: ((ae >> 8) & 0x00FF00FF) | (ao & 0xFF00FF00)
-}
-
-// The horizontal taps of a word whose support crosses the left / right image border (replicate border in x: clamped pixel
-// index per byte).  Only the first and last couple of threads of a row take it, but inlined and unrolled into every one of
-// the K x NV copies of the row step it made the kernel 127 registers (3 CTAs per SM) and large enough to miss the instruction
-// cache (ncu: no-instruction stalls, instruction-cache requests 79 % of peak) — so: one rolled, out-of-line copy.
 // Replicate border in x without an edge path: after a row has landed, the warp that owns the first word of the row writes
 // the 16 halo bytes left of it (bytes at row position p < 0 are channel p mod C of pixel 0 — a byte permutation of the row's
 // first word), and the warp that owns the last word writes the 16 bytes right of it (channel q mod C of the last pixel — a
@@ -346,11 +330,14 @@ __global__ void __launch_bounds__(U8S_THREADS) blur_u8_stream_kernel(const uint8
         // K-deep register window of H-pass results, oldest first.  The row loop is NOT unrolled: rotating the window costs
         // (K-1)*NV register moves per row, whereas K unrolled copies of the row step made the kernel ~40 KB of code that
         // missed the instruction cache on every lap (ncu: no-instruction stalls, icache requests 45-79 % of peak).
-        uint32_t win[K][NV];
+        // Q8 path: the window keeps each H result SPLIT into its even and odd bytes (two 16-bit lanes per register: exactly the
+        // operand form of the V pass), so the V pass is ten IMADs and one PRMT per word — no byte extraction (the kernel is bound
+        // by the ALU pipe: LOP / PRMT / SHF).  The binomial path (K = 3) keeps packed bytes in win alone.
+        uint32_t win[K][NV], wodd[K][NV];
 #pragma unroll
         for (int s = 0; s < K; ++s)
 #pragma unroll
-            for (int v = 0; v < NV; ++v) win[s][v] = 0u;
+            for (int v = 0; v < NV; ++v) { win[s][v] = 0u; wodd[s][v] = 0u; }
         const int iy_end = y_end + HY;
 #pragma unroll 1
         for (int iy = y_first - HY; iy < iy_end; ++iy) {
@@ -376,10 +363,10 @@ __global__ void __launch_bounds__(U8S_THREADS) blur_u8_stream_kernel(const uint8
                 }
                 __syncwarp();
             }
-            uint32_t hres[NV];
+            uint32_t hres[NV], hodd[NV];
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                hres[v] = 0;
+                hres[v] = 0; hodd[v] = 0;
                 if (act[v]) {
                     uint32_t x[7];
                     // tap t of output bytes B..B+3 starts at row byte B + (t - HX)*C: word index and shift are compile-time
@@ -393,7 +380,18 @@ __global__ void __launch_bounds__(U8S_THREADS) blur_u8_stream_kernel(const uint8
                         const int sh = off - 4 * wi;                            // 0..3
                         x[t] = sh == 0 ? wp[wi] : __funnelshift_r(wp[wi], wp[wi + 1], 8 * sh);
                     }
-                    hres[v] = binomial ? avg4_round_up(avg4_round_up(x[0], x[1]), avg4_round_up(x[1], x[2])) : u8s_q8_lanes(x, kx, K);
+                    if (binomial) hres[v] = avg4_round_up(avg4_round_up(x[0], x[1]), avg4_round_up(x[1], x[2]));
+                    else {
+                        uint32_t ae = 0x00800080u, ao = 0x00800080u;         // + 128 per 16-bit lane
+#pragma unroll
+                        for (int t = 0; t < 7; ++t) {
+                            if (t >= K) break;
+                            ae += (x[t] & 0x00FF00FFu) * kx[t];
+                            ao += __byte_perm(x[t], 0u, 0x4341u) * kx[t];
+                        }
+                        hres[v] = __byte_perm(ae, 0u, 0x4341u);              // (ae >> 8) & 0x00FF00FF: result bytes 0 and 2
+                        hodd[v] = __byte_perm(ao, 0u, 0x4341u);              // result bytes 1 and 3
+                    }
                 }
             }
             __syncwarp();
@@ -402,18 +400,22 @@ __global__ void __launch_bounds__(U8S_THREADS) blur_u8_stream_kernel(const uint8
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
 #pragma unroll
-                for (int s = 0; s + 1 < K; ++s) win[s][v] = win[s + 1][v];
-                win[K - 1][v] = hres[v];
+                for (int s = 0; s + 1 < K; ++s) { win[s][v] = win[s + 1][v]; wodd[s][v] = wodd[s + 1][v]; }
+                win[K - 1][v] = hres[v]; wodd[K - 1][v] = hodd[v];
             }
             // output row r = iy - HY is complete: its window is win[0..K-1]
             if (iy - HY >= y_first) {
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     if (!act[v]) continue;
-                    uint32_t y[7];
+                    uint32_t o;
+                    if (binomial) o = avg4_round_up(avg4_round_up(win[0][v], win[1][v]), avg4_round_up(win[1][v], win[K > 2 ? 2 : 0][v]));
+                    else {
+                        uint32_t ve = 0x00800080u, vo = 0x00800080u;
 #pragma unroll
-                    for (int t = 0; t < 7; ++t) y[t] = t < K ? win[t][v] : 0u;
-                    const uint32_t o = binomial ? avg4_round_up(avg4_round_up(y[0], y[1]), avg4_round_up(y[1], y[2])) : u8s_q8_lanes(y, ky, K);
+                        for (int t = 0; t < K; ++t) { ve += win[t][v] * ky[t]; vo += wodd[t][v] * ky[t]; }
+                        o = __byte_perm(ve, vo, 0x7351u);                    // high byte of each lane, even / odd interleaved
+                    }
                     *reinterpret_cast<uint32_t*>(out + B[v]) = o;
                 }
                 out += P.rowb;
@@ -439,7 +441,9 @@ static int launch_blur_u8_stream(cudaStream_t s, const uint8_t* src, uint8_t* ds
     const int per_sm = std::min(resident, knob(KNOB_C) > 0 ? knob(KNOB_C) : 8);
     const size_t ctas = (size_t)device_info().sm_count * per_sm;
     const size_t total = (size_t)P.strips * batch * rows;
-    uint32_t rc = knob(KNOB_D) > 0 ? (uint32_t)knob(KNOB_D) : (uint32_t)std::max<size_t>(32, total / (ctas * 12));
+    // rows per chunk: every chunk re-reads K-1 halo rows, so long chunks when there is enough work for ~4 units per CTA (16 x 4K:
+    // 32 rows 0.384 ms, 128 rows 0.368 ms), short ones otherwise
+    uint32_t rc = knob(KNOB_D) > 0 ? (uint32_t)knob(KNOB_D) : (uint32_t)std::min<size_t>(128, std::max<size_t>(32, total / (ctas * 4)));
     rc = std::min(rc, rows);
     P.rows_per_chunk = rc;
     P.chunks = (rows + rc - 1) / rc;
