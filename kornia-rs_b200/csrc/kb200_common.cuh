@@ -33,7 +33,13 @@ enum Knob {
     KNOB_WARP_PF, KNOB_WARP_PATH,                           // warp.cu: prefetch rows (-1 = off); forced path (1 gather, 2 tiled, 3 stream)
     KNOB_WS_STAGES, KNOB_WS_CTAS, KNOB_WS_RC, KNOB_WS_NPX,  // warp_stream
     KNOB_RS_STAGES, KNOB_RS_CTAS, KNOB_RS_NPX,              // resize_rows_f32
-    KNOB_A, KNOB_B, KNOB_C, KNOB_D,                         // scratch knobs for experiments
+    // A/B switches of the tests and tools (0 = shipped choice):
+    //   a  f32 warps / remap: 3 round-2 x4 kernel, 2 the same with the shared reciprocal, 4 lean kernel general path only,
+    //      5 lean kernel with STG stores, 7 lean kernel with four 1-D row copies per warp, 6 remap thread-per-pixel kernel
+    //   b  u8 samplers: 1 byte taps / clamped sampler everywhere, 2 word taps in remap_u8's general path; u8 blur: 3 tile kernel
+    //   c  u8 warps: 32-pixel segments per warp; u8 blur: CTAs per SM
+    //   d  u8 blur: rows per chunk
+    KNOB_A, KNOB_B, KNOB_C, KNOB_D,
     KNOB_COUNT
 };
 int knob(Knob k);
